@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json on B200: rows/s and fraction of HBM roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline workload (BASELINE.json configs[1], "C2"): SELECT a FROM t WHERE a > 0.5 over 1e8
+synthetic Float64 rows per GPU — the fused predicate + order-preserving filter-gather kernel.
+A "step" is one pass of that operator over one 1e8-row batch.  Rows are partitioned by row range
+across ranks (no data-path collective for filter/project), so scaling is weak: every rank filters
+its own 1e8-row batch and `value` is the total rows of all ranks / max-over-ranks device time.
+
+  value     device-resident: the batch is already in HBM when the timed region starts
+  e2e       through the C ABI with HOST buffers: H2D of the batch from pinned memory, the kernel,
+            and D2H of the compacted result into pinned memory, every step
+  roofline  algorithmic bytes of the dominant kernel (8*N read + 8*N_sel written) / its average
+            duration measured with CUDA events recorded around the launch on the launching stream
+  extra     the other single-GPU BASELINE configs (C3 fused expr+filter, C4 hash GROUP BY; with N>1
+            C4 includes the NCCL partial-aggregate merge), same timing rules
+  cpu_baseline  the CPU oracle (C++ restatement of the reference's single-threaded operators) on a
+            bounded sample of the same workload, on this box's host cores (rank 0, N=1 only)
+
+--impl reference times that CPU restatement alone (the reference is Rust; no toolchain here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "rows/s filter+agg over 1e8-row Arrow batch (C2: SELECT a FROM t WHERE a>0.5, Float64)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    """Returns (rank, world, local_rank, torch or None)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1, 0, None
+    import torch
+    import torch.distributed as dist
+    rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", os.environ["RANK"]))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, torch
+
+
+def barrier(torch):
+    if torch is not None:
+        import torch.distributed as dist
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def max_over_ranks(torch, x):
+    if torch is None:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(torch, x):
+    if torch is None:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def time_steps(ctx, torch, fn, steps, warmup):
+    """W untimed warm-ups, then exactly K steps between barrier+sync, device events, max over ranks."""
+    for _ in range(warmup):
+        fn()
+    ctx.sync()
+    barrier(torch)
+    ctx.profile_enable(True)
+    l0 = ctx.kernel_launches()
+    ctx.timer_start()
+    for _ in range(steps):
+        fn()
+    ms = ctx.timer_stop()
+    ctx.sync()
+    barrier(torch)
+    kms, kn = ctx.profile_get()
+    ctx.profile_enable(False)
+    return max_over_ranks(torch, ms), kms, kn, ctx.kernel_launches() - l0
+
+
+def run_ours(args):
+    from datafusion_archive_b200 import engine, workloads
+    rank, world, local, torch = dist_setup(args.gpus)
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N>1)" % (args.gpus, world))
+    ctx = engine.GpuContext(local)
+    peak, peak_src = hbm_peak()
+    n = args.rows
+    steps, warmup = args.steps, max(3, args.warmup)
+
+    # ---- C2 (headline) -----------------------------------------------------------------------
+    pin_in = engine.PinnedBuffer((n,), np.float64)
+    arrays, pred, proj = workloads.c2(n, seed=42 + rank, out=pin_in.array)
+    a = arrays[0]
+    n_sel = int(np.count_nonzero(a > 0.5))
+    pin_out = engine.PinnedBuffer((n,), np.float64)
+    batch = ctx.upload([a])
+    state = {}
+
+    def step_resident():
+        r = ctx.filter_project(batch, pred, proj)
+        state["nrows"] = r.nrows
+        r.free()
+
+    def step_e2e():
+        b = ctx.upload([a])
+        r = ctx.filter_project(b, pred, proj)
+        r.copy_into(0, pin_out.array)
+        state["nrows"] = r.nrows
+        r.free()
+        b.free()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, kms, kn, launches = time_steps(ctx, torch, step_resident, steps, warmup)
+    clocks = sampler.stop()
+    assert state["nrows"] == n_sel, "GPU row count %d != expected %d" % (state["nrows"], n_sel)
+    total_rows = sum_over_ranks(torch, float(n))
+    value = total_rows * steps / (ms / 1e3)
+    kernel_ms = kms / max(1, kn)
+    alg_bytes = 8.0 * n + 8.0 * n_sel
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    e2e_steps = max(3, min(steps, 10))
+    ems, _, _, _ = time_steps(ctx, torch, step_e2e, e2e_steps, 3)
+    assert np.array_equal(pin_out.array[:n_sel][:1000], a[a > 0.5][:1000])
+    e2e_value = total_rows * e2e_steps / (ems / 1e3)
+    batch.free()
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: SELECT a FROM t WHERE a > 0.5; a~U[0,1) Float64, %d rows per GPU, seed 42+rank" % n,
+                   "rows_per_gpu": n, "selectivity": n_sel / n, "partitioning": "row-range, one batch per rank, no collective",
+                   "l2": "inputs (%.1f GB per step) larger than L2 (126 MB); no explicit flush" % (8.0 * n / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n_sel + 32,
+                "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
+                "path": "dfgpu_batch_upload(pinned host) -> dfgpu_filter_project -> dfgpu_result_copy_col(pinned host)"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_filter_project", "kernel_ms": kernel_ms,
+                     "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+    }
+
+    # ---- extras: C3 and C4 (same timing rules; failures are recorded, not fatal) ----------------
+    extra = {}
+    xs = max(3, min(steps, 10))
+    try:
+        arrays3, pred3, proj3 = workloads.c3(n, seed=142 + 10 * rank)
+        b3 = ctx.upload(arrays3)
+        sel3 = int(np.count_nonzero(arrays3[1] < arrays3[0]))
+
+        def step3():
+            r = ctx.filter_project(b3, pred3, proj3)
+            state["n3"] = r.nrows
+            r.free()
+        ms3, kms3, kn3, _ = time_steps(ctx, torch, step3, xs, 3)
+        assert state["n3"] == sel3
+        k3 = kms3 / max(1, kn3)
+        bytes3 = 16.0 * n + 16.0 * sel3
+        extra["c3"] = {"workload": "C3: SELECT a+b, a*b FROM t WHERE b<a; 4 Float64 cols", "value": total_rows * xs / (ms3 / 1e3),
+                       "unit": "rows/s", "ms_per_step": ms3 / xs, "kernel_ms": k3,
+                       "roofline": {"bound": "hbm", "achieved": bytes3 / (k3 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": bytes3 / (k3 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes3}}
+        b3.free()
+        del arrays3
+    except Exception as e:  # pragma: no cover
+        extra["c3"] = {"error": repr(e)}
+    try:
+        arrays4, keys4, aggs4, _ = workloads.c4(n, seed=46 + 10 * rank)
+        b4 = ctx.upload(arrays4)
+        if world > 1:
+            import torch.distributed as dist
+            uid = [engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            ctx.comm_init(rank, world, uid[0])
+
+        def step4():
+            r = ctx.aggregate(b4, keys4, aggs4)
+            state["g4"] = r.nrows
+            r.free()
+        ms4, kms4, kn4, _ = time_steps(ctx, torch, step4, xs, 3)
+        assert state["g4"] == 100_000, state["g4"]
+        k4 = kms4 / max(1, kn4)
+        bytes4 = 16.0 * n
+        extra["c4"] = {"workload": "C4: SELECT k, SUM(v), COUNT(v) FROM t GROUP BY k; 1e5 Int64 keys" + (" + NCCL partial-aggregate merge" if world > 1 else ""),
+                       "value": total_rows * xs / (ms4 / 1e3), "unit": "rows/s", "ms_per_step": ms4 / xs, "kernel_ms": k4,
+                       "roofline": {"bound": "hbm", "achieved": bytes4 / (k4 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": bytes4 / (k4 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes4, "kernel": "k_hash_agg"}}
+        b4.free()
+        del arrays4
+    except Exception as e:  # pragma: no cover
+        extra["c4"] = {"error": repr(e)}
+    out["extra"] = extra
+
+    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(a, pred, proj, budget_s=12.0)
+    ctx.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if torch is not None:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def cpu_baseline(a, pred, proj, budget_s):
+    """The oracle (kind "port": the reference is Rust, not buildable here) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    cal = min(len(a), 4_000_000)
+    t0 = time.perf_counter()
+    O.filter_project([a[:cal]], pred, proj)
+    rate = cal / (time.perf_counter() - t0)
+    sample = int(min(len(a), max(cal, rate * budget_s / 3)))
+    times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        O.filter_project([a[:sample]], pred, proj)
+        times.append(time.perf_counter() - t0)
+    return {"value": sample / float(np.median(times)), "unit": "rows/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "first %d rows of the C2 batch, one batch, median of 3 passes; single thread = the reference's execution model "
+                      "(README.md:20; Rc/RefCell operators are !Send)" % sample}
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's operators on the host cores."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    from datafusion_archive_b200 import workloads
+    n = args.rows
+    sample = min(n, args.ref_sample)
+    arrays, pred, proj = workloads.c2(sample, seed=42)
+    steps, warmup = args.steps, max(1, min(args.warmup, 3))
+    for _ in range(warmup):
+        O.filter_project(arrays, pred, proj)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.filter_project(arrays, pred, proj)
+    dt = time.perf_counter() - t0
+    value = sample * steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: SELECT a FROM t WHERE a > 0.5; a~U[0,1) Float64, %d rows per GPU, seed 42+rank" % n, "rows_per_gpu": n},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": "each step = the first %d rows of the C2 batch through oracle/df_oracle.cpp (C++ restatement; the reference is "
+                                   "Rust and cannot be built in this image); 1 thread = the reference's execution model" % sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
+    ap.add_argument("--ref-sample", type=int, default=20_000_000, help="rows per step of the reference arm")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

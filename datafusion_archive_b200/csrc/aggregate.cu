@@ -1,0 +1,863 @@
+// aggregate.cu — AggregateRelation on the GPU (K4 column reduce, K5 hash-aggregate, K7 table
+// compaction, K6 partial-aggregate merge of SURVEY.md §2b).
+//
+// Reference path replaced: `with_group_by` (src/execution/aggregate.rs:787-952) — per row a
+// heap-allocated Vec<GroupByScalar> key, an FNV hash-map lookup, and a boxed ScalarValue folded
+// through Rc<RefCell<dyn AggregateFunction>> (aggregate.rs:548-612, 102-283) — and
+// `without_group_by` (aggregate.rs:703-785).  Here the map is an open-addressed table in HBM
+// (linear probing, 64-bit packed keys claimed with atomicCAS) whose accumulators are updated with
+// fire-and-forget L2 reductions: RED.ADD.F64 for f64 SUM, RED.ADD.U64 for COUNT / integer SUM,
+// RED.MIN/MAX.U64 on an order-preserving encoding for MIN/MAX (bit-exact for every type).
+#include <memory>
+
+#include "expr_vm.cuh"
+
+namespace dfgpu {
+
+constexpr int AG_THREADS = 256;
+constexpr int AG_R = 4;
+constexpr int AG_TILE = AG_THREADS * AG_R;
+constexpr int kMaxAggs = 8;
+constexpr int kMaxKeys = 4;
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+constexpr int AG_MAX_PROBE = 1 << 14;
+constexpr long long AG_MIN_CAP = 1ll << 22;
+
+struct AggDesc {
+  uint8_t func;   // DFGPU_AGG_*
+  uint8_t mtype;  // machine type of the argument
+  uint8_t dtype;  // Arrow dtype of the argument
+  uint8_t out_dtype;
+};
+
+struct AggParams {
+  ProgramSet ps;  // programs [0,nkeys) = group keys, [nkeys, nkeys+naggs) = aggregate arguments
+  AggDesc aggs[kMaxAggs];
+  unsigned long long key_mask[kMaxKeys];
+  int key_shift[kMaxKeys];
+  int nkeys, naggs;
+  long long nrows;
+  const unsigned* row_list;  // non-null: process rows row_list[0..nlist) (overflow replay)
+  long long nlist;
+  unsigned long long* keys;  // [cap+1]; slot cap is reserved for the key that equals EMPTY_KEY
+  unsigned long long* vals;  // [naggs][cap+1]
+  long long cap;             // power of two
+  long long max_groups;      // new keys are refused (-> overflow list) beyond this fill
+  unsigned long long* counters;  // [0] ngroups [1] overflow count [2] sentinel-key used [3] error
+  unsigned* ovf_rows;
+};
+
+// ---- order-preserving encodings so that MIN/MAX are native u64 atomics -----------------------
+__device__ __forceinline__ unsigned long long ord_enc(unsigned long long v, int mt) {
+  switch (mt) {
+    case MT_F64: return (v >> 63) ? ~v : (v ^ 0x8000000000000000ull);
+    case MT_F32: { unsigned b = (unsigned)v; return (b >> 31) ? (unsigned long long)(~b) : (unsigned long long)(b ^ 0x80000000u); }
+    case MT_I: return v ^ 0x8000000000000000ull;
+    default: return v;
+  }
+}
+__host__ __device__ __forceinline__ unsigned long long ord_dec(unsigned long long e, int mt) {
+  switch (mt) {
+    case MT_F64: return (e >> 63) ? (e ^ 0x8000000000000000ull) : ~e;
+    case MT_F32: { unsigned b = (unsigned)e; return (b >> 31) ? (unsigned long long)(b ^ 0x80000000u) : (unsigned long long)(~b); }
+    case MT_I: return e ^ 0x8000000000000000ull;
+    default: return e;
+  }
+}
+__device__ __forceinline__ bool is_nan_val(unsigned long long v, int mt) {
+  if (mt == MT_F64) { double d = u2d(v); return d != d; }
+  if (mt == MT_F32) { float f = u2f(v); return f != f; }
+  return false;
+}
+__host__ __device__ __forceinline__ unsigned long long agg_identity(int func) {
+  return func == DFGPU_AGG_MIN ? ~0ull : 0ull;
+}
+
+// fold one value into an accumulator held in a register / shared memory
+__device__ __forceinline__ unsigned long long acc_fold(int func, int mt, unsigned long long acc, unsigned long long v) {
+  switch (func) {
+    case DFGPU_AGG_SUM:
+      if (mt == MT_F64) return d2u(u2d(acc) + u2d(v));
+      if (mt == MT_F32) return f2u(u2f(acc) + u2f(v));
+      return acc + v;
+    case DFGPU_AGG_COUNT: return acc + 1ull;
+    case DFGPU_AGG_MIN: {
+      if (is_nan_val(v, mt)) return acc;  // f64::min ignores NaN (aggregate.rs:139-140)
+      unsigned long long e = ord_enc(v, mt);
+      return e < acc ? e : acc;
+    }
+    default: {
+      if (is_nan_val(v, mt)) return acc;
+      unsigned long long e = ord_enc(v, mt);
+      return e > acc ? e : acc;
+    }
+  }
+}
+// combine two accumulators
+__device__ __forceinline__ unsigned long long acc_merge(int func, int mt, unsigned long long a, unsigned long long b) {
+  switch (func) {
+    case DFGPU_AGG_SUM:
+      if (mt == MT_F64) return d2u(u2d(a) + u2d(b));
+      if (mt == MT_F32) return f2u(u2f(a) + u2f(b));
+      return a + b;
+    case DFGPU_AGG_COUNT: return a + b;
+    case DFGPU_AGG_MIN: return a < b ? a : b;
+    default: return a > b ? a : b;
+  }
+}
+// combine an accumulator into global memory (fire-and-forget reductions)
+__device__ __forceinline__ void acc_merge_global(int func, int mt, unsigned long long* p, unsigned long long b) {
+  switch (func) {
+    case DFGPU_AGG_SUM:
+      if (mt == MT_F64) atomicAdd((double*)p, u2d(b));
+      else if (mt == MT_F32) atomicAdd((float*)p, u2f(b));
+      else atomicAdd(p, b);
+      break;
+    case DFGPU_AGG_COUNT: atomicAdd(p, b); break;
+    case DFGPU_AGG_MIN: atomicMin(p, b); break;
+    default: atomicMax(p, b); break;
+  }
+}
+// fold one raw value into global memory
+__device__ __forceinline__ void acc_fold_global(int func, int mt, unsigned long long* p, unsigned long long v) {
+  switch (func) {
+    case DFGPU_AGG_SUM:
+      if (mt == MT_F64) atomicAdd((double*)p, u2d(v));
+      else if (mt == MT_F32) atomicAdd((float*)p, u2f(v));
+      else atomicAdd(p, v);
+      break;
+    case DFGPU_AGG_COUNT: atomicAdd(p, 1ull); break;
+    case DFGPU_AGG_MIN:
+      if (!is_nan_val(v, mt)) atomicMin(p, ord_enc(v, mt));
+      break;
+    default:
+      if (!is_nan_val(v, mt)) atomicMax(p, ord_enc(v, mt));
+      break;
+  }
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// Find the slot of `key`, claiming an empty one when the key is new.  Returns -1 when the key is
+// new and the table refuses new keys (fill limit / probe limit): the row goes to the overflow list.
+__device__ __forceinline__ long long probe_insert(unsigned long long* keys, long long cap, unsigned long long key,
+                                                  unsigned long long first_cur, unsigned long long h, bool full,
+                                                  unsigned& new_groups) {
+  const unsigned long long mask = (unsigned long long)cap - 1ull;
+  unsigned long long cur = first_cur;
+  for (int probes = 0; probes < AG_MAX_PROBE; ++probes) {
+    if (cur == key) return (long long)h;
+    if (cur == EMPTY_KEY) {
+      if (full) return -1;
+      const unsigned long long old = atomicCAS(&keys[h], EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { new_groups++; return (long long)h; }
+      if (old == key) return (long long)h;
+    }
+    h = (h + 1ull) & mask;
+    cur = __ldcg(&keys[h]);
+  }
+  return -1;
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__ AggParams p) {
+  __shared__ int s_full;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long n = p.row_list ? p.nlist : p.nrows;
+  const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  const long long stride = p.cap + 1;
+  bool bad = false;
+  for (long long tb = (long long)blockIdx.x * AG_TILE; tb < n; tb += (long long)gridDim.x * AG_TILE) {
+    if (tid == 0) s_full = (long long)__ldcg(&p.counters[0]) >= p.max_groups;
+    __syncthreads();
+    const bool full = s_full != 0;
+    long long rows[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      const long long i = tb + (long long)r * AG_THREADS + tid;
+      rows[r] = i < n ? (p.row_list ? (long long)p.row_list[i] : i) : -1;
+    }
+    // group key: one packed 64-bit word (GroupByScalar vector of aggregate.rs:807-852)
+    unsigned long long key[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) key[r] = 0;
+    for (int k = 0; k < p.nkeys; k++) {
+      unsigned long long v[AG_R];
+      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, k, rows, v);
+      bad = bad || (b != 0);
+#pragma unroll
+      for (int r = 0; r < AG_R; r++) key[r] |= (v[r] & p.key_mask[k]) << p.key_shift[k];
+    }
+    // first probe of all R rows issued back to back (R independent L2 requests in flight)
+    unsigned long long h[AG_R], cur[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      h[r] = mix64(key[r]) & hmask;
+      cur[r] = (rows[r] >= 0 && key[r] != EMPTY_KEY) ? __ldcg(&p.keys[h[r]]) : 0ull;
+    }
+    long long slot[AG_R];
+    unsigned new_groups = 0;
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      if (rows[r] < 0) { slot[r] = -1; continue; }
+      if (key[r] == EMPTY_KEY) {  // the one key value that collides with the empty marker
+        if (__ldcg(&p.counters[2]) == 0ull) p.counters[2] = 1ull;
+        slot[r] = p.cap;
+        continue;
+      }
+      slot[r] = probe_insert(p.keys, p.cap, key[r], cur[r], h[r], full, new_groups);
+      if (slot[r] < 0) {
+        const unsigned long long at = atomicAdd(&p.counters[1], 1ull);
+        p.ovf_rows[at] = (unsigned)rows[r];
+      }
+    }
+    // accumulators (update_accumulators, aggregate.rs:548-612): argument evaluated once per row
+    for (int a = 0; a < p.naggs; a++) {
+      unsigned long long v[AG_R];
+      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, p.nkeys + a, rows, v);
+      const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
+      unsigned long long* col = p.vals + (long long)a * stride;
+#pragma unroll
+      for (int r = 0; r < AG_R; r++) {
+        if (slot[r] >= 0) {
+          acc_fold_global(func, mt, col + slot[r], v[r]);
+          if ((b >> r) & 1u) bad = true;
+        }
+      }
+    }
+    // one counter update per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+    if (lane == 0 && new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+    __syncthreads();
+  }
+  if (bad) p.counters[3] = 1ull;
+}
+
+// K4: no GROUP BY.  Per-thread accumulators live in shared memory (one 8-byte cell per thread per
+// aggregate, conflict-free), block-reduced at the end, one global reduction per CTA per aggregate.
+template <int DEPTH>
+__global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ AggParams p) {
+  __shared__ unsigned long long s_acc[kMaxAggs][AG_THREADS];
+  __shared__ unsigned long long s_red[AG_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int a = 0; a < p.naggs; a++) s_acc[a][tid] = agg_identity(p.aggs[a].func);
+  bool bad = false;
+  for (long long tb = (long long)blockIdx.x * AG_TILE; tb < p.nrows; tb += (long long)gridDim.x * AG_TILE) {
+    long long rows[AG_R];
+#pragma unroll
+    for (int r = 0; r < AG_R; r++) {
+      const long long i = tb + (long long)r * AG_THREADS + tid;
+      rows[r] = i < p.nrows ? i : -1;
+    }
+    for (int a = 0; a < p.naggs; a++) {
+      unsigned long long v[AG_R];
+      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, a, rows, v);
+      bad = bad || (b != 0);
+      const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
+      unsigned long long acc = s_acc[a][tid];
+#pragma unroll
+      for (int r = 0; r < AG_R; r++)
+        if (rows[r] >= 0) acc = acc_fold(func, mt, acc, v[r]);
+      s_acc[a][tid] = acc;
+    }
+  }
+  for (int a = 0; a < p.naggs; a++) {
+    const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
+    unsigned long long acc = s_acc[a][tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc = acc_merge(func, mt, acc, __shfl_xor_sync(0xffffffffu, acc, o));
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      acc = lane < AG_THREADS / 32 ? s_red[lane] : agg_identity(func);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc = acc_merge(func, mt, acc, __shfl_xor_sync(0xffffffffu, acc, o));
+      if (lane == 0) acc_merge_global(func, mt, p.vals + a, acc);  // cap == 0: vals[a][0]
+    }
+    __syncthreads();
+  }
+  if (bad) p.counters[3] = 1ull;
+}
+
+// K7: scan the table, emit occupied slots densely.  raw != 0 keeps packed keys / undecoded
+// accumulators (the exchange format of the multi-GPU merge).
+struct CompactParams {
+  const unsigned long long* keys;
+  const unsigned long long* vals;
+  long long cap;
+  int sentinel_used;
+  int nkeys, naggs, raw;
+  AggDesc aggs[kMaxAggs];
+  unsigned long long key_mask[kMaxKeys];
+  int key_shift[kMaxKeys];
+  int key_dtype[kMaxKeys];
+  void* out_keys[kMaxKeys];
+  void* out_vals[kMaxAggs];
+  unsigned long long* counter;
+};
+
+__global__ void __launch_bounds__(256) k_compact(const __grid_constant__ CompactParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long stride = p.cap + 1;
+  const long long total = p.cap + 1;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  // round the loop bound up to a warp multiple so ballots stay converged
+  for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < total; s0 += step) {
+    const long long s = s0 + threadIdx.x;
+    bool occ = false;
+    unsigned long long key = 0;
+    if (s < p.cap) { key = p.keys[s]; occ = key != EMPTY_KEY; }
+    else if (s == p.cap) { key = EMPTY_KEY; occ = p.sentinel_used != 0; }
+    const unsigned m = __ballot_sync(0xffffffffu, occ);
+    if (!m) continue;
+    unsigned long long basei = 0;
+    if (lane == 0) basei = atomicAdd(p.counter, (unsigned long long)__popc(m));
+    basei = __shfl_sync(0xffffffffu, basei, 0);
+    if (!occ) continue;
+    const long long idx = (long long)(basei + __popc(m & ((1u << lane) - 1u)));
+    if (p.raw) {
+      ((unsigned long long*)p.out_keys[0])[idx] = key;
+      for (int a = 0; a < p.naggs; a++) ((unsigned long long*)p.out_vals[a])[idx] = p.vals[(long long)a * stride + s];
+    } else {
+      for (int k = 0; k < p.nkeys; k++) {
+        unsigned long long v = (key >> p.key_shift[k]) & p.key_mask[k];
+        store_elem(p.out_keys[k], p.key_dtype[k], idx, v);
+      }
+      for (int a = 0; a < p.naggs; a++) {
+        unsigned long long v = p.vals[(long long)a * stride + s];
+        const int f = p.aggs[a].func;
+        if (f == DFGPU_AGG_MIN || f == DFGPU_AGG_MAX) v = ord_dec(v, p.aggs[a].mtype);
+        store_elem(p.out_vals[a], p.aggs[a].out_dtype, idx, v);
+      }
+    }
+  }
+}
+
+// Re-insert (raw key, raw accumulators) entries into a table: used to grow the table and to merge
+// the partial aggregates of other GPUs (K6).
+struct MergeParams {
+  const unsigned long long* in_keys;
+  const unsigned long long* in_vals[kMaxAggs];
+  long long n;
+  unsigned long long* keys;
+  unsigned long long* vals;
+  long long cap;
+  int naggs;
+  AggDesc aggs[kMaxAggs];
+  unsigned long long* counters;
+};
+
+__global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergeParams p) {
+  const long long stride = p.cap + 1;
+  const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  unsigned new_groups = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = p.in_keys[i];
+    long long slot;
+    if (key == EMPTY_KEY) {
+      p.counters[2] = 1ull;
+      slot = p.cap;
+    } else {
+      const unsigned long long h = mix64(key) & hmask;
+      slot = probe_insert(p.keys, p.cap, key, __ldcg(&p.keys[h]), h, false, new_groups);
+      if (slot < 0) { p.counters[3] = 2ull; continue; }  // cannot happen: caller sizes the table
+    }
+    for (int a = 0; a < p.naggs; a++)
+      acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.vals + (long long)a * stride + slot, p.in_vals[a][i]);
+  }
+  if (new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+}
+
+}  // namespace dfgpu
+
+using namespace dfgpu;
+
+// ---------------------------------------------------------------------------------------------
+// host state of one AggregateRelation
+// ---------------------------------------------------------------------------------------------
+struct dfgpu_aggstate {
+  dfgpu_ctx* ctx = nullptr;
+  std::vector<std::vector<dfgpu_insn>> key_progs;
+  std::vector<std::vector<dfgpu_insn>> arg_progs;
+  std::vector<int> funcs, out_dtypes;
+  int nkeys = 0, naggs = 0;
+  // resolved at the first update
+  bool typed = false;
+  std::vector<int> key_dtypes;
+  std::vector<int> key_shift;
+  std::vector<unsigned long long> key_mask;
+  std::vector<AggDesc> descs;
+  // table
+  long long cap = 0;
+  long long expected = 0;
+  unsigned long long* d_keys = nullptr;
+  unsigned long long* d_vals = nullptr;
+  unsigned long long* d_counters = nullptr;  // 8 x u64
+  long long ngroups = 0;
+  bool sentinel_used = false;
+  long long rows_seen = 0;
+  bool finished = false;
+
+  ~dfgpu_aggstate() {
+    if (ctx) {
+      ctx->free(d_keys);
+      ctx->free(d_vals);
+      ctx->free(d_counters);
+    }
+  }
+};
+
+namespace {
+
+long long next_pow2(long long x) {
+  long long p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+void table_alloc(dfgpu_ctx* ctx, int naggs, const std::vector<AggDesc>& descs, long long cap, unsigned long long** keys,
+                 unsigned long long** vals) {
+  const size_t stride = size_t(cap + 1);
+  *keys = (unsigned long long*)ctx->alloc(stride * 8);
+  *vals = (unsigned long long*)ctx->alloc(stride * 8 * size_t(naggs > 0 ? naggs : 1));
+  DF_CUDA(cudaMemsetAsync(*keys, 0xff, stride * 8, ctx->stream));
+  for (int a = 0; a < naggs; a++)
+    DF_CUDA(cudaMemsetAsync(*vals + size_t(a) * stride, descs[size_t(a)].func == DFGPU_AGG_MIN ? 0xff : 0x00, stride * 8, ctx->stream));
+}
+
+void read_counters(dfgpu_aggstate* st, unsigned long long* host4) {
+  dfgpu_ctx* ctx = st->ctx;
+  DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 4; i++) host4[i] = ctx->h_scratch[8 + i];
+}
+
+int grid_for(dfgpu_ctx* ctx, long long work_items, int per_block, int blocks_per_sm) {
+  long long g = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)ctx->sm_count * blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return int(g);
+}
+
+// grow the table to new_cap, re-inserting every occupied slot
+void table_grow(dfgpu_aggstate* st, long long new_cap) {
+  dfgpu_ctx* ctx = st->ctx;
+  unsigned long long *nk, *nv;
+  table_alloc(ctx, st->naggs, st->descs, new_cap, &nk, &nv);
+  // compact raw, then merge into the new table
+  const size_t cnt = size_t(st->ngroups + 1);
+  unsigned long long* ck = (unsigned long long*)ctx->alloc(cnt * 8);
+  unsigned long long* cv = (unsigned long long*)ctx->alloc(cnt * 8 * size_t(st->naggs > 0 ? st->naggs : 1));
+  CompactParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.keys = st->d_keys;
+  cp.vals = st->d_vals;
+  cp.cap = st->cap;
+  cp.sentinel_used = st->sentinel_used;
+  cp.nkeys = st->nkeys;
+  cp.naggs = st->naggs;
+  cp.raw = 1;
+  cp.out_keys[0] = ck;
+  for (int a = 0; a < st->naggs; a++) {
+    cp.aggs[a] = st->descs[size_t(a)];
+    cp.out_vals[a] = cv + size_t(a) * cnt;
+  }
+  DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
+  cp.counter = st->d_counters + 4;
+  k_compact<<<grid_for(ctx, st->cap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
+  DF_CUDA(cudaGetLastError());
+  ctx->launches++;
+  MergeParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.in_keys = ck;
+  for (int a = 0; a < st->naggs; a++) {
+    mp.in_vals[a] = cv + size_t(a) * cnt;
+    mp.aggs[a] = st->descs[size_t(a)];
+  }
+  mp.n = st->ngroups + (st->sentinel_used ? 1 : 0);
+  mp.keys = nk;
+  mp.vals = nv;
+  mp.cap = new_cap;
+  mp.naggs = st->naggs;
+  DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 8, ctx->stream));  // ngroups is recounted by the merge
+  mp.counters = st->d_counters;
+  if (mp.n > 0) {
+    k_merge<<<grid_for(ctx, mp.n, 256, 8), 256, 0, ctx->stream>>>(mp);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->free(ck);
+  ctx->free(cv);
+  ctx->free(st->d_keys);
+  ctx->free(st->d_vals);
+  st->d_keys = nk;
+  st->d_vals = nv;
+  st->cap = new_cap;
+}
+
+template <int DEPTH>
+void launch_hash_agg(dfgpu_ctx* ctx, const AggParams& p, long long n) {
+  int per_sm = 0;
+  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hash_agg<DEPTH>, AG_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int ps = ctx->prof_begin();
+  k_hash_agg<DEPTH><<<grid_for(ctx, n, AG_TILE, per_sm), AG_THREADS, 0, ctx->stream>>>(p);
+  DF_CUDA(cudaGetLastError());
+  ctx->prof_end(ps);
+  ctx->launches++;
+}
+template <int DEPTH>
+void launch_reduce(dfgpu_ctx* ctx, const AggParams& p, long long n) {
+  int per_sm = 0;
+  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce<DEPTH>, AG_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  const int ps = ctx->prof_begin();
+  k_reduce<DEPTH><<<grid_for(ctx, n, AG_TILE, per_sm), AG_THREADS, 0, ctx->stream>>>(p);
+  DF_CUDA(cudaGetLastError());
+  ctx->prof_end(ps);
+  ctx->launches++;
+}
+
+}  // namespace
+
+extern "C" int dfgpu_aggregate_create(dfgpu_ctx* ctx, const dfgpu_insn* const* keys, const int* key_len, int nkeys,
+                                      const dfgpu_agg* aggs, int naggs, int64_t expected_groups, dfgpu_aggstate** out) {
+  return guarded([&] {
+    if (!ctx || !out) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_create: null argument");
+    if (nkeys < 0 || nkeys > kMaxKeys) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than " + std::to_string(kMaxKeys) + " GROUP BY expressions");
+    if (naggs < 1) fail(DFGPU_ERR_GENERAL, "aggregate needs at least one aggregate expression");
+    if (naggs > kMaxAggs) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than " + std::to_string(kMaxAggs) + " aggregate expressions");
+    ctx->use();
+    auto st = std::make_unique<dfgpu_aggstate>();
+    st->ctx = ctx;
+    st->nkeys = nkeys;
+    st->naggs = naggs;
+    st->expected = expected_groups;
+    for (int k = 0; k < nkeys; k++) st->key_progs.emplace_back(keys[k], keys[k] + key_len[k]);
+    for (int a = 0; a < naggs; a++) {
+      // compile_expr accepts min/max/count/sum (expression.rs:98-107); anything else is
+      // General("Unsupported aggregate function ...")
+      if (aggs[a].func < DFGPU_AGG_MIN || aggs[a].func > DFGPU_AGG_COUNT)
+        fail(DFGPU_ERR_GENERAL, "Unsupported aggregate function '" + std::to_string(aggs[a].func) + "'");
+      st->arg_progs.emplace_back(aggs[a].arg, aggs[a].arg + aggs[a].arg_len);
+      st->funcs.push_back(aggs[a].func);
+      st->out_dtypes.push_back(aggs[a].out_dtype);
+    }
+    st->d_counters = (unsigned long long*)ctx->alloc(64);
+    DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 64, ctx->stream));
+    *out = st.release();
+  });
+}
+
+extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
+  return guarded([&] {
+    if (!st || !batch) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_update: null argument");
+    if (st->finished) fail(DFGPU_ERR_GENERAL, "aggregate already finished");
+    dfgpu_ctx* ctx = st->ctx;
+    ctx->use();
+    for (const auto& c : batch->cols)
+      if (c.null_count > 0) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
+    if (batch->nrows >= (1ll << 32)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "batches of 2^32 rows or more");
+
+    AggParams p;
+    memset(&p, 0, sizeof(p));
+    ProgramBuilder pb(batch);
+    std::vector<int> kdt;
+    for (int k = 0; k < st->nkeys; k++) {
+      int pi = pb.add(st->key_progs[size_t(k)].data(), int(st->key_progs[size_t(k)].size()), "GROUP BY expression");
+      int dt = pb.out_dtype(pi);
+      if (dt == DFGPU_UTF8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys are not supported on the GPU path yet");
+      if (!is_int(dt)) fail(DFGPU_ERR_EXECUTION, "Unsupported GROUP BY data type");  // aggregate.rs:848-850
+      kdt.push_back(dt);
+    }
+    std::vector<AggDesc> descs;
+    for (int a = 0; a < st->naggs; a++) {
+      int pi = pb.add(st->arg_progs[size_t(a)].data(), int(st->arg_progs[size_t(a)].size()), "aggregate argument");
+      int dt = pb.out_dtype(pi);
+      if (!is_numeric(dt)) fail(DFGPU_ERR_EXECUTION, std::string("Unsupported data type for aggregate: ") + dtype_name(dt));
+      AggDesc d;
+      d.func = uint8_t(st->funcs[size_t(a)]);
+      d.mtype = mtype_of(dt);
+      d.dtype = uint8_t(dt);
+      int want = d.func == DFGPU_AGG_COUNT ? DFGPU_UINT64 : dt;
+      int odt = st->out_dtypes[size_t(a)];
+      if (odt == 0) odt = want;
+      if (odt != want)  // the reference would hit "unexpected type when creating array from aggregate map" (aggregate.rs:683-695)
+        fail(DFGPU_ERR_EXECUTION, "unexpected type when creating array from aggregate map");
+      d.out_dtype = uint8_t(odt);
+      descs.push_back(d);
+    }
+    if (!st->typed) {
+      st->key_dtypes = kdt;
+      st->descs = descs;
+      int bits = 0;
+      for (int k = st->nkeys - 1; k >= 0; k--) {  // last key in the low bits
+        int w = dtype_width(kdt[size_t(k)]) * 8;
+        st->key_shift.insert(st->key_shift.begin(), bits);
+        st->key_mask.insert(st->key_mask.begin(), w == 64 ? ~0ull : ((1ull << w) - 1ull));
+        bits += w;
+      }
+      if (bits > 64) fail(DFGPU_ERR_NOT_IMPLEMENTED, "composite GROUP BY keys wider than 64 bits");
+      if (st->nkeys == 1) st->key_mask[0] = ~0ull;  // single key: keep the sign-extended 64-bit value
+      st->typed = true;
+      st->cap = st->nkeys == 0 ? 0 : std::max(AG_MIN_CAP, next_pow2(2 * st->expected));
+      table_alloc(ctx, st->naggs, st->descs, st->cap, &st->d_keys, &st->d_vals);
+    } else {
+      if (kdt != st->key_dtypes) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
+      for (int a = 0; a < st->naggs; a++)
+        if (descs[size_t(a)].dtype != st->descs[size_t(a)].dtype) fail(DFGPU_ERR_GENERAL, "aggregate argument types changed between batches");
+    }
+    pb.finish(&p.ps);
+    for (int s = 0; s < p.ps.ncols; s++)
+      if (!is_numeric(p.ps.cols[s].dtype))
+        fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("expressions over ") + dtype_name(p.ps.cols[s].dtype) + " columns are not supported on the GPU path yet");
+    if (p.ps.max_depth > 8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression too deep (register stack depth > 8)");
+    st->rows_seen += batch->nrows;
+    if (batch->nrows == 0) return;
+
+    p.nkeys = st->nkeys;
+    p.naggs = st->naggs;
+    for (int a = 0; a < st->naggs; a++) p.aggs[a] = st->descs[size_t(a)];
+    for (int k = 0; k < st->nkeys; k++) {
+      p.key_mask[k] = st->key_mask[size_t(k)];
+      p.key_shift[k] = st->key_shift[size_t(k)];
+    }
+    p.nrows = batch->nrows;
+    p.counters = st->d_counters;
+    const int d = p.ps.max_depth;
+
+    if (st->nkeys == 0) {
+      p.keys = st->d_keys;
+      p.vals = st->d_vals;
+      p.cap = 0;
+      if (d <= 1) launch_reduce<1>(ctx, p, p.nrows);
+      else if (d <= 2) launch_reduce<2>(ctx, p, p.nrows);
+      else if (d <= 4) launch_reduce<4>(ctx, p, p.nrows);
+      else launch_reduce<8>(ctx, p, p.nrows);
+      unsigned long long c[4];
+      read_counters(st, c);
+      if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
+      return;
+    }
+
+    // GROUP BY: run, then replay rows that could not get a slot after growing the table
+    unsigned* ovf[2] = {(unsigned*)ctx->alloc(size_t(batch->nrows) * 4), nullptr};
+    struct Freer {
+      dfgpu_ctx* c;
+      unsigned** o;
+      ~Freer() { c->free(o[0]); c->free(o[1]); }
+    } freer{ctx, ovf};
+    int cur = 0;
+    const unsigned* list = nullptr;
+    long long nlist = 0;
+    for (int round = 0;; round++) {
+      if (round > 40) fail(DFGPU_ERR_INTERNAL, "hash table growth did not converge");
+      p.keys = st->d_keys;
+      p.vals = st->d_vals;
+      p.cap = st->cap;
+      p.max_groups = st->cap / 2;
+      p.row_list = list;
+      p.nlist = nlist;
+      p.ovf_rows = ovf[cur];
+      DF_CUDA(cudaMemsetAsync(st->d_counters + 1, 0, 8, ctx->stream));
+      const long long n = list ? nlist : p.nrows;
+      if (d <= 1) launch_hash_agg<1>(ctx, p, n);
+      else if (d <= 2) launch_hash_agg<2>(ctx, p, n);
+      else if (d <= 4) launch_hash_agg<4>(ctx, p, n);
+      else launch_hash_agg<8>(ctx, p, n);
+      unsigned long long c[4];
+      read_counters(st, c);
+      if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
+      st->ngroups = (long long)c[0];
+      st->sentinel_used = c[2] != 0;
+      const long long novf = (long long)c[1];
+      if (novf == 0) {
+        if (st->ngroups > st->cap / 2) table_grow(st, st->cap * 4);  // keep the load factor low for the next batch
+        break;
+      }
+      table_grow(st, st->cap * 4);
+      list = ovf[cur];
+      nlist = novf;
+      cur ^= 1;
+      if (!ovf[cur]) ovf[cur] = (unsigned*)ctx->alloc(size_t(batch->nrows) * 4);
+    }
+  });
+}
+
+// Exchange hooks used by the communicator (api.cu): raw compaction of the local table and merge of
+// remote entries.  Declared here, defined below.
+namespace dfgpu {
+void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n);
+void agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n, long long val_stride);
+void agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st);
+int agg_naggs(const dfgpu_aggstate* st) { return st->naggs; }
+// api.cu (NCCL)
+void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
+                       unsigned long long* d_vals);
+}  // namespace dfgpu
+
+void dfgpu::agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
+  int funcs[kMaxAggs], mtypes[kMaxAggs];
+  for (int a = 0; a < st->naggs; a++) {
+    funcs[a] = st->descs[size_t(a)].func;
+    mtypes[a] = st->descs[size_t(a)].mtype;
+  }
+  agg_exchange_impl(ctx, st, &st->rows_seen, st->nkeys, funcs, mtypes, st->d_vals);
+}
+
+void dfgpu::agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n) {
+  dfgpu_ctx* ctx = st->ctx;
+  const long long cnt = st->nkeys == 0 ? 1 : st->ngroups + (st->sentinel_used ? 1 : 0);
+  const size_t alloc_n = size_t(cnt > 0 ? cnt : 1);
+  *keys = (unsigned long long*)ctx->alloc(alloc_n * 8);
+  *vals = (unsigned long long*)ctx->alloc(alloc_n * 8 * size_t(st->naggs));
+  CompactParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.keys = st->d_keys;
+  cp.vals = st->d_vals;
+  cp.cap = st->cap;
+  cp.sentinel_used = st->nkeys == 0 ? 1 : (st->sentinel_used ? 1 : 0);
+  cp.nkeys = st->nkeys;
+  cp.naggs = st->naggs;
+  cp.raw = 1;
+  cp.out_keys[0] = *keys;
+  for (int a = 0; a < st->naggs; a++) {
+    cp.aggs[a] = st->descs[size_t(a)];
+    cp.out_vals[a] = *vals + size_t(a) * alloc_n;
+  }
+  DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
+  cp.counter = st->d_counters + 4;
+  k_compact<<<grid_for(ctx, st->cap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
+  DF_CUDA(cudaGetLastError());
+  ctx->launches++;
+  *n = cnt;
+}
+
+void dfgpu::agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n,
+                          long long val_stride) {
+  dfgpu_ctx* ctx = st->ctx;
+  if (n <= 0) return;
+  if (st->nkeys > 0 && (st->ngroups + n) * 2 > st->cap) table_grow(st, next_pow2((st->ngroups + n) * 4));
+  MergeParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.in_keys = keys;
+  for (int a = 0; a < st->naggs; a++) {
+    mp.in_vals[a] = vals + size_t(a) * size_t(val_stride);
+    mp.aggs[a] = st->descs[size_t(a)];
+  }
+  mp.n = n;
+  mp.keys = st->d_keys;
+  mp.vals = st->d_vals;
+  mp.cap = st->cap;
+  mp.naggs = st->naggs;
+  mp.counters = st->d_counters;
+  k_merge<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mp);
+  DF_CUDA(cudaGetLastError());
+  ctx->launches++;
+  unsigned long long c[4];
+  read_counters(st, c);
+  if (c[3]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed");
+  st->ngroups = (long long)c[0];
+  st->sentinel_used = c[2] != 0;
+}
+
+extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
+  return guarded([&] {
+    if (!st || !out) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_finish: null argument");
+    if (st->finished) fail(DFGPU_ERR_GENERAL, "aggregate already finished");  // one-shot (aggregate.rs:616-619)
+    dfgpu_ctx* ctx = st->ctx;
+    ctx->use();
+    if (!st->typed) {
+      // no batch was ever seen: resolve types from the declared output types
+      if (st->nkeys > 0) {
+        // an empty GROUP BY input yields an empty batch; key types are unknown -> need a batch
+        fail(DFGPU_ERR_GENERAL, "aggregate finished before any input batch was provided");
+      }
+      for (int a = 0; a < st->naggs; a++) {
+        AggDesc d;
+        int odt = st->out_dtypes[size_t(a)];
+        if (!is_numeric(odt)) fail(DFGPU_ERR_GENERAL, "aggregate output type must be given when there is no input");
+        d.func = uint8_t(st->funcs[size_t(a)]);
+        d.dtype = uint8_t(odt);
+        d.mtype = mtype_of(odt);
+        d.out_dtype = uint8_t(odt);
+        st->descs.push_back(d);
+      }
+      st->typed = true;
+      st->cap = 0;
+      table_alloc(ctx, st->naggs, st->descs, 0, &st->d_keys, &st->d_vals);
+    }
+    if (ctx->world > 1) {
+      // every rank must take part, and ranks reduce row counts too (null-ness of the global result)
+      agg_exchange(ctx, st);
+    }
+    auto res = std::make_unique<dfgpu_result>();
+    res->ctx = ctx;
+    const long long cnt = st->nkeys == 0 ? 1 : st->ngroups + (st->sentinel_used ? 1 : 0);
+    const size_t alloc_n = size_t(cnt > 0 ? cnt : 1);
+    CompactParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.keys = st->d_keys;
+    cp.vals = st->d_vals;
+    cp.cap = st->cap;
+    cp.sentinel_used = st->nkeys == 0 ? 1 : (st->sentinel_used ? 1 : 0);
+    cp.nkeys = st->nkeys;
+    cp.naggs = st->naggs;
+    cp.raw = 0;
+    for (int k = 0; k < st->nkeys; k++) {  // group columns first (aggregate.rs:890-925)
+      DevColumn c;
+      c.dtype = st->key_dtypes[size_t(k)];
+      c.values_bytes = alloc_n * size_t(dtype_width(c.dtype));
+      c.values = ctx->alloc(c.values_bytes);
+      res->cols.push_back(c);
+      cp.out_keys[k] = c.values;
+      cp.key_dtype[k] = c.dtype;
+      cp.key_mask[k] = st->key_mask[size_t(k)];
+      cp.key_shift[k] = st->key_shift[size_t(k)];
+    }
+    for (int a = 0; a < st->naggs; a++) {  // then aggregate columns (aggregate.rs:928-949)
+      DevColumn c;
+      c.dtype = st->descs[size_t(a)].out_dtype;
+      c.values_bytes = alloc_n * size_t(dtype_width(c.dtype));
+      c.values = ctx->alloc(c.values_bytes);
+      res->cols.push_back(c);
+      cp.out_vals[a] = c.values;
+      cp.aggs[a] = st->descs[size_t(a)];
+    }
+    DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
+    cp.counter = st->d_counters + 4;
+    k_compact<<<grid_for(ctx, st->cap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
+    res->nrows = cnt;
+    if (st->nkeys == 0 && st->rows_seen == 0) {
+      // no input rows: every aggregate is null (array_from_scalar!, aggregate.rs:641-643)
+      for (auto& c : res->cols) {
+        c.validity = (uint8_t*)ctx->alloc(1);
+        DF_CUDA(cudaMemsetAsync(c.validity, 0, 1, ctx->stream));
+        c.null_count = 1;
+      }
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    st->finished = true;
+    *out = res.release();
+  });
+}
+
+extern "C" int dfgpu_aggregate_free(dfgpu_aggstate* st) {
+  return guarded([&] {
+    if (st) st->ctx->use();
+    delete st;
+  });
+}

@@ -1,0 +1,608 @@
+// api.cu — context, memory, batch upload, result download, timing and the NCCL communicator of the
+// C ABI declared in include/dfgpu.h.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "common.cuh"
+
+namespace dfgpu {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+const char* dtype_name(int dt) {
+  switch (dt) {
+    case DFGPU_BOOL: return "Boolean";
+    case DFGPU_INT8: return "Int8";
+    case DFGPU_INT16: return "Int16";
+    case DFGPU_INT32: return "Int32";
+    case DFGPU_INT64: return "Int64";
+    case DFGPU_UINT8: return "UInt8";
+    case DFGPU_UINT16: return "UInt16";
+    case DFGPU_UINT32: return "UInt32";
+    case DFGPU_UINT64: return "UInt64";
+    case DFGPU_FLOAT32: return "Float32";
+    case DFGPU_FLOAT64: return "Float64";
+    case DFGPU_UTF8: return "Utf8";
+  }
+  return "?";
+}
+
+int dtype_width(int dt) {
+  switch (dt) {
+    case DFGPU_INT8: case DFGPU_UINT8: return 1;
+    case DFGPU_INT16: case DFGPU_UINT16: return 2;
+    case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_FLOAT32: return 4;
+    case DFGPU_INT64: case DFGPU_UINT64: case DFGPU_FLOAT64: return 8;
+  }
+  return 0;
+}
+
+}  // namespace dfgpu
+
+using namespace dfgpu;
+
+// ---------------------------------------------------------------------------------------------
+// ctx
+// ---------------------------------------------------------------------------------------------
+void dfgpu_ctx::use() { DF_CUDA(cudaSetDevice(device)); }
+
+void* dfgpu_ctx::alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 8;
+  DF_CUDA(cudaMallocAsync(&p, bytes, stream));  // stream-ordered pool: freed blocks are reused without a driver call
+  return p;
+}
+
+void dfgpu_ctx::free(void* p) {
+  if (p) cudaFreeAsync(p, stream);
+}
+
+int dfgpu_ctx::prof_begin() {
+  if (!prof_on) return -1;
+  const int s = prof_next;
+  prof_next = (prof_next + 1) % kProfRing;
+  if (!prof_ev[s][0]) {
+    DF_CUDA(cudaEventCreate(&prof_ev[s][0]));
+    DF_CUDA(cudaEventCreate(&prof_ev[s][1]));
+  }
+  if (prof_pending[s]) {  // slot reuse: fold the old measurement in first (long finished)
+    float ms = 0;
+    DF_CUDA(cudaEventSynchronize(prof_ev[s][1]));
+    DF_CUDA(cudaEventElapsedTime(&ms, prof_ev[s][0], prof_ev[s][1]));
+    prof_ms += ms;
+    prof_n++;
+    prof_pending[s] = false;
+  }
+  DF_CUDA(cudaEventRecord(prof_ev[s][0], stream));
+  return s;
+}
+void dfgpu_ctx::prof_end(int s) {
+  if (s < 0) return;
+  DF_CUDA(cudaEventRecord(prof_ev[s][1], stream));
+  prof_pending[s] = true;
+}
+void dfgpu_ctx::prof_drain() {
+  for (int s = 0; s < kProfRing; s++) {
+    if (!prof_pending[s]) continue;
+    float ms = 0;
+    DF_CUDA(cudaEventSynchronize(prof_ev[s][1]));
+    DF_CUDA(cudaEventElapsedTime(&ms, prof_ev[s][0], prof_ev[s][1]));
+    prof_ms += ms;
+    prof_n++;
+    prof_pending[s] = false;
+  }
+}
+
+extern "C" int dfgpu_profile_enable(dfgpu_ctx* ctx, int on) {
+  return guarded([&] {
+    ctx->use();
+    ctx->prof_drain();
+    ctx->prof_on = on != 0;
+    ctx->prof_ms = 0.0;
+    ctx->prof_n = 0;
+  });
+}
+extern "C" int dfgpu_profile_get(dfgpu_ctx* ctx, double* kernel_ms, int64_t* launches) {
+  return guarded([&] {
+    ctx->use();
+    ctx->prof_drain();
+    *kernel_ms = ctx->prof_ms;
+    *launches = ctx->prof_n;
+  });
+}
+
+dfgpu_batch::~dfgpu_batch() {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& c : cols) {
+    ctx->free(c.values);
+    ctx->free(c.validity);
+    ctx->free(c.offsets);
+  }
+}
+dfgpu_result::~dfgpu_result() {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto& c : cols) {
+    ctx->free(c.values);
+    ctx->free(c.validity);
+    ctx->free(c.offsets);
+  }
+}
+
+extern "C" int dfgpu_abi_version(void) { return DFGPU_ABI_VERSION; }
+extern "C" const char* dfgpu_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int dfgpu_device_count(int* out) {
+  return guarded([&] {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      n = 0;
+    }
+    *out = n;
+  });
+}
+
+extern "C" int dfgpu_init(int device, dfgpu_ctx** out) {
+  return guarded([&] {
+    if (!out) fail(DFGPU_ERR_GENERAL, "dfgpu_init: null out");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      fail(DFGPU_ERR_CUDA, "no CUDA device available: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= n) fail(DFGPU_ERR_CUDA, "device ordinal " + std::to_string(device) + " out of range");
+    auto ctx = std::make_unique<dfgpu_ctx>();
+    ctx->device = device;
+    ctx->use();
+    cudaDeviceProp prop;
+    DF_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      fail(DFGPU_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+                               "; this library is built for sm_100a (B200) only");
+    ctx->sm_count = prop.multiProcessorCount;
+    DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DF_CUDA(cudaEventCreate(&ctx->ev_start));
+    DF_CUDA(cudaEventCreate(&ctx->ev_stop));
+    // keep freed blocks cached in the stream-ordered pool
+    cudaMemPool_t pool;
+    DF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thresh = ~0ull;
+    DF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    DF_CUDA(cudaMalloc(&ctx->d_scratch, 64 * 8));
+    DF_CUDA(cudaMemset(ctx->d_scratch, 0, 64 * 8));
+    DF_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * 8));
+    *out = ctx.release();
+  });
+}
+
+extern "C" int dfgpu_comm_destroy(dfgpu_ctx* ctx);
+
+extern "C" int dfgpu_shutdown(dfgpu_ctx* ctx) {
+  return guarded([&] {
+    if (!ctx) return;
+    ctx->use();
+    cudaStreamSynchronize(ctx->stream);
+    dfgpu_comm_destroy(ctx);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    for (int i = 0; i < 2; i++) {
+      if (ctx->stage[i]) cudaFreeHost(ctx->stage[i]);
+      if (ctx->stage_ev[i]) cudaEventDestroy(ctx->stage_ev[i]);
+    }
+    for (int i = 0; i < dfgpu_ctx::kProfRing; i++)
+      for (int j = 0; j < 2; j++)
+        if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
+    cudaFree(ctx->d_scratch);
+    cudaFreeHost(ctx->h_scratch);
+    cudaEventDestroy(ctx->ev_start);
+    cudaEventDestroy(ctx->ev_stop);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+  });
+}
+
+extern "C" int dfgpu_sync(dfgpu_ctx* ctx) {
+  return guarded([&] {
+    ctx->use();
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+extern "C" int dfgpu_host_alloc(size_t bytes, void** out) {
+  return guarded([&] { DF_CUDA(cudaMallocHost(out, bytes ? bytes : 8)); });
+}
+extern "C" int dfgpu_host_free(void* p) {
+  return guarded([&] {
+    if (p) DF_CUDA(cudaFreeHost(p));
+  });
+}
+
+extern "C" int dfgpu_timer_start(dfgpu_ctx* ctx) {
+  return guarded([&] {
+    ctx->use();
+    DF_CUDA(cudaEventRecord(ctx->ev_start, ctx->stream));
+  });
+}
+extern "C" int dfgpu_timer_stop(dfgpu_ctx* ctx, float* ms) {
+  return guarded([&] {
+    ctx->use();
+    DF_CUDA(cudaEventRecord(ctx->ev_stop, ctx->stream));
+    DF_CUDA(cudaEventSynchronize(ctx->ev_stop));
+    DF_CUDA(cudaEventElapsedTime(ms, ctx->ev_start, ctx->ev_stop));
+  });
+}
+
+extern "C" int dfgpu_flush_l2(dfgpu_ctx* ctx) {
+  return guarded([&] {
+    ctx->use();
+    if (!ctx->flush_buf) {
+      ctx->flush_bytes = size_t(256) << 20;  // 2x the 126 MB L2
+      DF_CUDA(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    DF_CUDA(cudaMemsetAsync(ctx->flush_buf, 0x5a, ctx->flush_bytes, ctx->stream));
+  });
+}
+
+extern "C" int dfgpu_kernel_launches(const dfgpu_ctx* ctx, int64_t* out) {
+  *out = ctx->launches;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// host -> device.  Pinned sources are one DMA; pageable sources are pipelined through two pinned
+// staging buffers (memcpy of chunk i+1 overlaps the DMA of chunk i).
+void h2d(dfgpu_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return;
+  if (is_pinned(src)) {
+    DF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return;
+  }
+  if (!ctx->stage[0]) {
+    ctx->stage_bytes = size_t(32) << 20;
+    for (int i = 0; i < 2; i++) {
+      DF_CUDA(cudaMallocHost(&ctx->stage[i], ctx->stage_bytes));
+      DF_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    }
+  }
+  size_t off = 0;
+  int i = 0;
+  while (off < bytes) {
+    size_t n = std::min(ctx->stage_bytes, bytes - off);
+    DF_CUDA(cudaEventSynchronize(ctx->stage_ev[i]));  // previous DMA out of this buffer is done
+    memcpy(ctx->stage[i], static_cast<const uint8_t*>(src) + off, n);
+    DF_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dst) + off, ctx->stage[i], n, cudaMemcpyHostToDevice, ctx->stream));
+    DF_CUDA(cudaEventRecord(ctx->stage_ev[i], ctx->stream));
+    off += n;
+    i ^= 1;
+  }
+}
+
+// copy `len` bits starting at bit `offset` into a fresh byte vector whose bit 0 is the first one
+std::vector<uint8_t> rebase_bits(const uint8_t* bits, int64_t offset, int64_t len) {
+  std::vector<uint8_t> out(size_t((len + 7) / 8), 0);
+  if ((offset & 7) == 0) {
+    memcpy(out.data(), bits + (offset >> 3), out.size());
+  } else {
+    for (int64_t i = 0; i < len; i++)
+      if ((bits[(offset + i) >> 3] >> ((offset + i) & 7)) & 1) out[size_t(i >> 3)] |= uint8_t(1u << (i & 7));
+  }
+  if (len & 7) out.back() &= uint8_t((1u << (len & 7)) - 1u);
+  return out;
+}
+
+}  // namespace
+
+extern "C" int dfgpu_batch_upload(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, dfgpu_batch** out) {
+  return guarded([&] {
+    if (!ctx || !out || (ncols > 0 && !cols)) fail(DFGPU_ERR_GENERAL, "dfgpu_batch_upload: null argument");
+    ctx->use();
+    auto b = std::make_unique<dfgpu_batch>();
+    b->ctx = ctx;
+    b->nrows = ncols > 0 ? cols[0].len : 0;
+    for (int i = 0; i < ncols; i++) {
+      const dfgpu_col& c = cols[i];
+      if (c.len != b->nrows) fail(DFGPU_ERR_GENERAL, "all columns of a RecordBatch must have the same length");
+      if (c.len < 0 || c.offset < 0) fail(DFGPU_ERR_GENERAL, "negative length/offset");
+      DevColumn d;
+      d.dtype = c.dtype;
+      std::vector<uint8_t> tmp;
+      if (c.validity && c.len > 0) {
+        tmp = rebase_bits(c.validity, c.offset, c.len);
+        int64_t valid = 0;
+        for (uint8_t byte : tmp) valid += __builtin_popcount(byte);
+        d.null_count = c.len - valid;
+        if (d.null_count > 0) {
+          d.validity = (uint8_t*)ctx->alloc(tmp.size());
+          // tmp is pageable and short-lived: synchronous-safe copy through the staging path
+          h2d(ctx, d.validity, tmp.data(), tmp.size());
+          DF_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+      }
+      const int w = dtype_width(c.dtype);
+      if (w > 0) {
+        d.values_bytes = size_t(c.len) * size_t(w);
+        d.values = ctx->alloc(d.values_bytes);
+        if (c.len > 0) {
+          if (!c.values) fail(DFGPU_ERR_GENERAL, "null values buffer");
+          h2d(ctx, d.values, static_cast<const uint8_t*>(c.values) + size_t(c.offset) * size_t(w), d.values_bytes);
+        }
+      } else if (c.dtype == DFGPU_BOOL) {
+        std::vector<uint8_t> bits = c.len > 0 ? rebase_bits(static_cast<const uint8_t*>(c.values), c.offset, c.len) : std::vector<uint8_t>();
+        d.values_bytes = bits.size();
+        d.values = ctx->alloc(d.values_bytes);
+        if (!bits.empty()) {
+          h2d(ctx, d.values, bits.data(), bits.size());
+          DF_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+      } else if (c.dtype == DFGPU_UTF8) {
+        if (!c.offsets) fail(DFGPU_ERR_GENERAL, "Utf8 column without offsets buffer");
+        d.offsets = (int32_t*)ctx->alloc(size_t(c.len + 1) * 4);
+        h2d(ctx, d.offsets, c.offsets + c.offset, size_t(c.len + 1) * 4);
+        const int32_t lo = c.offsets[c.offset], hi = c.offsets[c.offset + c.len];
+        if (hi < lo || hi > c.values_bytes) fail(DFGPU_ERR_GENERAL, "corrupt Utf8 offsets");
+        // keep the whole byte buffer prefix so device offsets stay valid as given
+        d.values_bytes = size_t(hi);
+        d.values = ctx->alloc(d.values_bytes);
+        if (hi > 0) h2d(ctx, d.values, c.values, size_t(hi));
+      } else {
+        fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("unsupported column type ") + std::to_string(c.dtype));
+      }
+      b->cols.push_back(d);
+    }
+    // the call borrows the host buffers only for its duration
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = b.release();
+  });
+}
+
+extern "C" int dfgpu_batch_rows(const dfgpu_batch* b, int64_t* nrows) {
+  *nrows = b->nrows;
+  return 0;
+}
+extern "C" int dfgpu_batch_free(dfgpu_batch* b) {
+  return guarded([&] { delete b; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// results
+// ---------------------------------------------------------------------------------------------
+extern "C" int dfgpu_result_shape(const dfgpu_result* r, int64_t* nrows, int* ncols) {
+  *nrows = r->nrows;
+  *ncols = int(r->cols.size());
+  return 0;
+}
+extern "C" int dfgpu_result_col_dtype(const dfgpu_result* r, int i, int32_t* dtype) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    *dtype = r->cols[size_t(i)].dtype;
+  });
+}
+extern "C" int dfgpu_result_col_bytes(const dfgpu_result* r, int i, int64_t* nbytes) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    const DevColumn& c = r->cols[size_t(i)];
+    const int w = dtype_width(c.dtype);
+    *nbytes = w ? r->nrows * w : int64_t(c.values_bytes);
+  });
+}
+extern "C" int dfgpu_result_col_nulls(const dfgpu_result* r, int i, int64_t* nulls) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    *nulls = r->cols[size_t(i)].null_count;
+  });
+}
+extern "C" int dfgpu_result_copy_col(const dfgpu_result* r, int i, void* dst_values, uint8_t* dst_validity, int32_t* dst_offsets) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    dfgpu_ctx* ctx = r->ctx;
+    ctx->use();
+    const DevColumn& c = r->cols[size_t(i)];
+    const int w = dtype_width(c.dtype);
+    const size_t nb = w ? size_t(r->nrows) * size_t(w) : c.values_bytes;
+    if (nb && dst_values) DF_CUDA(cudaMemcpyAsync(dst_values, c.values, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst_validity) {
+      const size_t vb = size_t(r->nrows + 7) / 8;
+      if (c.validity) DF_CUDA(cudaMemcpyAsync(dst_validity, c.validity, vb, cudaMemcpyDeviceToHost, ctx->stream));
+      else memset(dst_validity, 0xff, vb);
+    }
+    if (dst_offsets && c.offsets)
+      DF_CUDA(cudaMemcpyAsync(dst_offsets, c.offsets, size_t(r->nrows + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+extern "C" int dfgpu_result_col_device_ptr(const dfgpu_result* r, int i, const void** dptr) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    *dptr = r->cols[size_t(i)].values;
+  });
+}
+extern "C" int dfgpu_result_free(dfgpu_result* r) {
+  return guarded([&] { delete r; });
+}
+
+// ---------------------------------------------------------------------------------------------
+// communicator: NCCL (loaded lazily so single-GPU use has no libnccl dependency)
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.h) return api;
+  // RTLD_NOLOAD first: reuse the copy a host application (e.g. torch) already mapped
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW);
+  if (!h) fail(DFGPU_ERR_CUDA, std::string("cannot load libnccl: ") + dlerror());
+#define LOAD(N)                                                     \
+  *(void**)(&api.N) = dlsym(h, "nccl" #N);                          \
+  if (!api.N) fail(DFGPU_ERR_CUDA, "libnccl is missing symbol nccl" #N);
+  LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllGather) LOAD(AllReduce) LOAD(GroupStart) LOAD(GroupEnd)
+  LOAD(GetErrorString)
+#undef LOAD
+  api.h = h;
+  return api;
+}
+
+#define DF_NCCL(expr)                                                                                        \
+  do {                                                                                                       \
+    ncclResult_t _r = (expr);                                                                                \
+    if (_r != ncclSuccess) fail(DFGPU_ERR_CUDA, std::string("NCCL error: ") + nccl().GetErrorString(_r) + " (" #expr ")"); \
+  } while (0)
+
+}  // namespace
+
+extern "C" int dfgpu_comm_unique_id(uint8_t out_id[128]) {
+  return guarded([&] {
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    DF_NCCL(nccl().GetUniqueId(&id));
+    memcpy(out_id, &id, 128);
+  });
+}
+
+extern "C" int dfgpu_comm_init(dfgpu_ctx* ctx, int rank, int world, const uint8_t nccl_unique_id[128]) {
+  return guarded([&] {
+    if (!ctx) fail(DFGPU_ERR_GENERAL, "dfgpu_comm_init: null ctx");
+    if (world < 1 || rank < 0 || rank >= world) fail(DFGPU_ERR_GENERAL, "bad rank/world");
+    ctx->use();
+    if (ctx->nccl_comm) fail(DFGPU_ERR_GENERAL, "communicator already initialised");
+    ctx->rank = rank;
+    ctx->world = world;
+    if (world == 1) return;
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    ncclComm_t comm;
+    DF_NCCL(nccl().CommInitRank(&comm, world, id, rank));
+    ctx->nccl_comm = comm;
+  });
+}
+
+extern "C" int dfgpu_comm_destroy(dfgpu_ctx* ctx) {
+  return guarded([&] {
+    if (ctx && ctx->nccl_comm) {
+      ctx->use();
+      nccl().CommDestroy((ncclComm_t)ctx->nccl_comm);
+      ctx->nccl_comm = nullptr;
+    }
+    if (ctx) {
+      ctx->world = 1;
+      ctx->rank = 0;
+    }
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// partial-aggregate merge across ranks.  Every rank ends with the global result
+// (all-reduce semantics).  No GROUP BY: a true ncclAllReduce per accumulator (SUM -> ncclSum,
+// COUNT -> ncclSum, MIN/MAX -> ncclMin/ncclMax on the order-preserving u64 encoding).  GROUP BY:
+// a sparse all-reduce = ncclAllGather of the compacted (key, accumulators) lists + a local merge
+// kernel (aggregate.cu: k_merge), because open-addressed slots are not canonical across ranks.
+// ---------------------------------------------------------------------------------------------
+struct dfgpu_aggstate;
+namespace dfgpu {
+void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n);
+void agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n, long long val_stride);
+int agg_naggs(const dfgpu_aggstate* st);
+void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
+                       unsigned long long* d_vals);
+}  // namespace dfgpu
+
+void dfgpu::agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs,
+                              const int* mtypes, unsigned long long* d_vals) {
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  if (!comm) fail(DFGPU_ERR_GENERAL, "world > 1 but no communicator");
+  const int W = ctx->world, naggs = agg_naggs(st);
+  NcclApi& N = nccl();
+  // counts: [n_local, rows_seen] per rank
+  unsigned long long* d_cnt = (unsigned long long*)ctx->alloc(size_t(2 * (W + 1)) * 8);
+  unsigned long long *keys = nullptr, *vals = nullptr;
+  long long n_local = 0;
+  if (nkeys > 0) agg_export_raw(st, &keys, &vals, &n_local);
+  ctx->h_scratch[16] = (unsigned long long)n_local;
+  ctx->h_scratch[17] = (unsigned long long)*rows_seen;
+  DF_CUDA(cudaMemcpyAsync(d_cnt, ctx->h_scratch + 16, 16, cudaMemcpyHostToDevice, ctx->stream));
+  DF_NCCL(N.AllGather(d_cnt, d_cnt + 2, 2, ncclUint64, comm, ctx->stream));
+  std::vector<unsigned long long> cnt(size_t(2 * W));
+  DF_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt + 2, size_t(2 * W) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->free(d_cnt);
+  long long total_rows = 0, max_n = 0;
+  for (int r = 0; r < W; r++) {
+    total_rows += (long long)cnt[size_t(2 * r + 1)];
+    max_n = std::max(max_n, (long long)cnt[size_t(2 * r)]);
+  }
+  *rows_seen = total_rows;
+  if (nkeys == 0) {
+    DF_NCCL(N.GroupStart());
+    for (int a = 0; a < naggs; a++) {
+      ncclDataType_t dt = ncclUint64;
+      ncclRedOp_t op = ncclSum;
+      if (funcs[a] == DFGPU_AGG_MIN) op = ncclMin;
+      else if (funcs[a] == DFGPU_AGG_MAX) op = ncclMax;
+      else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 1 /*MT_F64*/) dt = ncclFloat64;
+      else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 2 /*MT_F32*/) dt = ncclFloat32;
+      // f32 accumulators occupy the low 4 bytes of their 8-byte cell
+      DF_NCCL(N.AllReduce(d_vals + a, d_vals + a, 1, dt, op, comm, ctx->stream));
+    }
+    DF_NCCL(N.GroupEnd());
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  // payload: per rank (1 + naggs) arrays of max_n u64
+  const size_t per_rank = size_t(1 + naggs) * size_t(max_n);
+  if (max_n > 0) {
+    unsigned long long* send = (unsigned long long*)ctx->alloc(per_rank * 8);
+    unsigned long long* recv = (unsigned long long*)ctx->alloc(per_rank * 8 * size_t(W));
+    const size_t ln = size_t(n_local > 0 ? n_local : 1);
+    if (n_local > 0) {
+      DF_CUDA(cudaMemcpyAsync(send, keys, size_t(n_local) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      for (int a = 0; a < naggs; a++)
+        DF_CUDA(cudaMemcpyAsync(send + size_t(1 + a) * size_t(max_n), vals + size_t(a) * ln, size_t(n_local) * 8,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    DF_NCCL(N.AllGather(send, recv, per_rank, ncclUint64, comm, ctx->stream));
+    for (int r = 0; r < W; r++) {
+      if (r == ctx->rank) continue;
+      const unsigned long long* base = recv + size_t(r) * per_rank;
+      agg_merge_raw(st, base, base + size_t(max_n), (long long)cnt[size_t(2 * r)], max_n);
+    }
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->free(send);
+    ctx->free(recv);
+  }
+  ctx->free(keys);
+  ctx->free(vals);
+}

@@ -1,0 +1,118 @@
+// common.cuh — internals shared by the sm_100a engine's translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/dfgpu.h"
+
+namespace dfgpu {
+
+// ---------------------------------------------------------------------------------------------
+// errors: C++ exception inside the library, converted to (code, thread-local message) at the ABI.
+// ---------------------------------------------------------------------------------------------
+struct Error {
+  int code;
+  std::string msg;
+};
+[[noreturn]] inline void fail(int code, const std::string& m) { throw Error{code, m}; }
+
+void set_last_error(const std::string& m);
+
+#define DF_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      ::dfgpu::fail(_e == cudaErrorMemoryAllocation ? DFGPU_ERR_OOM : DFGPU_ERR_CUDA,              \
+                    std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + " (" #expr ")");                                \
+  } while (0)
+
+template <class Fn>
+int guarded(Fn&& fn) {
+  try {
+    fn();
+    return DFGPU_OK;
+  } catch (const Error& e) {
+    set_last_error(e.msg);
+    return e.code;
+  } catch (const std::exception& e) {
+    set_last_error(std::string("internal: ") + e.what());
+    return DFGPU_ERR_INTERNAL;
+  }
+}
+
+const char* dtype_name(int dt);
+int dtype_width(int dt);  // bytes; 0 for bool/utf8
+inline bool is_signed_int(int dt) { return dt >= DFGPU_INT8 && dt <= DFGPU_INT64; }
+inline bool is_unsigned_int(int dt) { return dt >= DFGPU_UINT8 && dt <= DFGPU_UINT64; }
+inline bool is_int(int dt) { return dt >= DFGPU_INT8 && dt <= DFGPU_UINT64; }
+inline bool is_float(int dt) { return dt == DFGPU_FLOAT32 || dt == DFGPU_FLOAT64; }
+inline bool is_numeric(int dt) { return dt >= DFGPU_INT8 && dt <= DFGPU_FLOAT64; }
+
+}  // namespace dfgpu
+
+// ---------------------------------------------------------------------------------------------
+// opaque handle definitions
+// ---------------------------------------------------------------------------------------------
+struct dfgpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  int64_t launches = 0;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  // device scratch shared by operators (error flags, counters); 64 x u64
+  unsigned long long* d_scratch = nullptr;
+  unsigned long long* h_scratch = nullptr;  // pinned mirror
+  // pinned staging ring for uploads from pageable memory
+  void* stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  // per-kernel profiling (dfgpu_profile_*): ring of event pairs around the dominant kernels
+  static constexpr int kProfRing = 32;
+  bool prof_on = false;
+  cudaEvent_t prof_ev[kProfRing][2] = {};
+  bool prof_pending[kProfRing] = {};
+  int prof_next = 0;
+  double prof_ms = 0.0;
+  int64_t prof_n = 0;
+  int prof_begin();          // returns ring slot or -1
+  void prof_end(int slot);
+  void prof_drain();
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* nccl_comm = nullptr;
+
+  void* alloc(size_t bytes);
+  void free(void* p);
+  void use();  // cudaSetDevice(device)
+};
+
+struct DevColumn {
+  int dtype = 0;
+  void* values = nullptr;        // device
+  size_t values_bytes = 0;
+  uint8_t* validity = nullptr;   // device, bit 0 = row 0 (re-based to offset 0), or null
+  int32_t* offsets = nullptr;    // utf8: device i32 offsets (re-based view keeps original values)
+  int64_t null_count = 0;
+};
+
+struct dfgpu_batch {
+  dfgpu_ctx* ctx = nullptr;
+  int64_t nrows = 0;
+  std::vector<DevColumn> cols;
+  ~dfgpu_batch();  // returns the column buffers to the ctx pool
+};
+
+struct dfgpu_result {
+  dfgpu_ctx* ctx = nullptr;
+  int64_t nrows = 0;
+  std::vector<DevColumn> cols;
+  ~dfgpu_result();
+};

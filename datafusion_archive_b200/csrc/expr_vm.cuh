@@ -1,0 +1,321 @@
+// expr_vm.cuh — the expression "compiler" and its device-side evaluator.
+//
+// The reference compiles an `Expr` tree into nested closures, one temporary Arrow array per node
+// and one N-row literal array per literal (src/execution/expression.rs:283-505, 226-243).  Here the
+// postfix program from the C ABI is type-checked on the host, lowered to a tiny register-stack
+// bytecode whose right-hand leaf operands (literals, columns) are folded into the consuming
+// instruction, and interpreted INSIDE the scan kernels, R rows per thread at a time, with the
+// operand stack held in registers.  All control flow of the interpreter is warp-uniform (every
+// thread runs the same program), so it costs a few scalar instructions per op per R rows; no
+// intermediate array is ever written to HBM.
+#pragma once
+#include "common.cuh"
+
+namespace dfgpu {
+
+enum MType : uint8_t { MT_NONE = 0, MT_F64 = 1, MT_F32 = 2, MT_I = 3, MT_U = 4, MT_BOOL = 5 };
+enum VOp : uint8_t {
+  V_PUSH_COL = 0, V_PUSH_IMM, V_CAST,
+  V_ADD, V_SUB, V_MUL, V_DIV,
+  V_EQ, V_NE, V_LT, V_LE, V_GT, V_GE,
+  V_AND, V_OR
+};
+enum RhsMode : uint8_t { RHS_STACK = 0, RHS_IMM = 1, RHS_COL = 2 };
+
+struct DevInsn {   // 16 bytes, lives in kernel parameter (constant) space
+  uint8_t op;      // VOp
+  uint8_t mode;    // RhsMode for binary ops
+  uint8_t mtype;   // machine type of the operands (CAST: of the source)
+  uint8_t dtype;   // Arrow dtype of the operands (int width for wrap-around); CAST: target dtype
+  int16_t slot;    // column slot for PUSH_COL / RHS_COL
+  int16_t aux;     // CAST: source dtype
+  unsigned long long imm;  // PUSH_IMM / RHS_IMM payload (raw bits, already widened)
+};
+
+constexpr int kMaxInsn = 96;
+constexpr int kMaxProgs = 24;
+constexpr int kMaxCols = 12;
+
+struct ColRef {
+  const void* ptr;
+  int dtype;
+  int _pad;
+};
+
+struct ProgramSet {
+  DevInsn insn[kMaxInsn];
+  ColRef cols[kMaxCols];
+  uint8_t start[kMaxProgs + 1];
+  uint8_t out_dtype[kMaxProgs];
+  int nprog;
+  int ncols;
+  int max_depth;
+};
+
+// ---- host side ----------------------------------------------------------------------------
+struct CompiledProgram {
+  std::vector<DevInsn> code;
+  int out_dtype = 0;
+  int max_depth = 0;
+  bool is_plain_column = false;  // program is exactly [PUSH_COL]
+  int plain_slot = -1;
+};
+
+class ProgramBuilder {
+ public:
+  explicit ProgramBuilder(const dfgpu_batch* batch) : batch_(batch) {}
+  // Type-check + lower one postfix program; appends to the set and returns its index.
+  int add(const dfgpu_insn* p, int n, const char* what);
+  int out_dtype(int prog) const { return progs_[size_t(prog)].out_dtype; }
+  const CompiledProgram& prog(int i) const { return progs_[size_t(i)]; }
+  int nprogs() const { return int(progs_.size()); }
+  // Finalise into the POD passed to kernels.
+  void finish(ProgramSet* out) const;
+  int slot_of_column(int col);
+
+ private:
+  const dfgpu_batch* batch_;
+  std::vector<CompiledProgram> progs_;
+  std::vector<int> slots_;  // slot -> batch column index
+};
+
+MType mtype_of(int dtype);
+
+#ifdef __CUDACC__
+// ---- device side ---------------------------------------------------------------------------
+__device__ __forceinline__ double u2d(unsigned long long x) { return __longlong_as_double((long long)x); }
+__device__ __forceinline__ unsigned long long d2u(double x) { return (unsigned long long)__double_as_longlong(x); }
+__device__ __forceinline__ float u2f(unsigned long long x) { return __uint_as_float((unsigned)x); }
+__device__ __forceinline__ unsigned long long f2u(float x) { return (unsigned long long)__float_as_uint(x); }
+
+// wrap a 64-bit integer result to the width of `dtype` (Rust release-mode wrapping arithmetic)
+__device__ __forceinline__ unsigned long long norm_int(unsigned long long x, int dtype) {
+  switch (dtype) {
+    case DFGPU_INT8: return (unsigned long long)(long long)(signed char)x;
+    case DFGPU_INT16: return (unsigned long long)(long long)(short)x;
+    case DFGPU_INT32: return (unsigned long long)(long long)(int)x;
+    case DFGPU_UINT8: return x & 0xffull;
+    case DFGPU_UINT16: return x & 0xffffull;
+    case DFGPU_UINT32: return x & 0xffffffffull;
+    default: return x;
+  }
+}
+
+// load element `row` of a column, widened to the 64-bit machine representation
+__device__ __forceinline__ unsigned long long load_elem(const void* p, int dtype, long long row) {
+  switch (dtype) {
+    case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64: return __ldg((const unsigned long long*)p + row);
+    case DFGPU_FLOAT32: case DFGPU_UINT32: return (unsigned long long)__ldg((const unsigned*)p + row);
+    case DFGPU_INT32: return (unsigned long long)(long long)__ldg((const int*)p + row);
+    case DFGPU_INT16: return (unsigned long long)(long long)__ldg((const short*)p + row);
+    case DFGPU_UINT16: return (unsigned long long)__ldg((const unsigned short*)p + row);
+    case DFGPU_INT8: return (unsigned long long)(long long)__ldg((const signed char*)p + row);
+    case DFGPU_UINT8: return (unsigned long long)__ldg((const unsigned char*)p + row);
+    default: return 0;
+  }
+}
+
+__device__ __forceinline__ void store_elem(void* p, int dtype, long long idx, unsigned long long v) {
+  switch (dtype) {
+    case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64: ((unsigned long long*)p)[idx] = v; break;
+    case DFGPU_FLOAT32: case DFGPU_UINT32: case DFGPU_INT32: ((unsigned*)p)[idx] = (unsigned)v; break;
+    case DFGPU_INT16: case DFGPU_UINT16: ((unsigned short*)p)[idx] = (unsigned short)v; break;
+    case DFGPU_INT8: case DFGPU_UINT8: ((unsigned char*)p)[idx] = (unsigned char)v; break;
+    default: break;
+  }
+}
+
+// Rust `as` (saturating float->int, NaN -> 0; wrapping int->int; nearest int->float)
+__device__ __forceinline__ unsigned long long cast_value(unsigned long long v, int src_mt, int src_dt, int dst_dt) {
+  // to floats
+  if (dst_dt == DFGPU_FLOAT64) {
+    switch (src_mt) {
+      case MT_F64: return v;
+      case MT_F32: return d2u((double)u2f(v));
+      case MT_I: return d2u((double)(long long)v);
+      default: return d2u((double)v);
+    }
+  }
+  if (dst_dt == DFGPU_FLOAT32) {
+    switch (src_mt) {
+      case MT_F64: return f2u((float)u2d(v));
+      case MT_F32: return v;
+      case MT_I: return f2u((float)(long long)v);
+      default: return f2u((float)v);
+    }
+  }
+  // to integers
+  if (src_mt == MT_F64 || src_mt == MT_F32) {
+    double x = src_mt == MT_F64 ? u2d(v) : (double)u2f(v);
+    if (x != x) return 0;
+    double lo, hi;
+    switch (dst_dt) {
+      case DFGPU_INT8: lo = -128.0; hi = 127.0; break;
+      case DFGPU_INT16: lo = -32768.0; hi = 32767.0; break;
+      case DFGPU_INT32: lo = -2147483648.0; hi = 2147483647.0; break;
+      case DFGPU_INT64: lo = -9223372036854775808.0; hi = 9223372036854775807.0; break;
+      case DFGPU_UINT8: lo = 0.0; hi = 255.0; break;
+      case DFGPU_UINT16: lo = 0.0; hi = 65535.0; break;
+      case DFGPU_UINT32: lo = 0.0; hi = 4294967295.0; break;
+      default: lo = 0.0; hi = 18446744073709551615.0; break;
+    }
+    if (dst_dt == DFGPU_UINT64) {
+      if (x <= lo) return 0;
+      if (x >= hi) return ~0ull;
+      return (unsigned long long)x;
+    }
+    if (dst_dt == DFGPU_INT64) {
+      if (x <= lo) return 0x8000000000000000ull;
+      if (x >= hi) return 0x7fffffffffffffffull;
+      return (unsigned long long)(long long)x;
+    }
+    if (x <= lo) x = lo;
+    if (x >= hi) x = hi;
+    return norm_int((unsigned long long)(long long)x, dst_dt);
+  }
+  return norm_int(v, dst_dt);  // int -> int: truncate / extend (value already sign/zero extended)
+}
+
+// Evaluate program [begin,end) of `ps` for R rows.  `rows[r]` is the row index of lane-row r, or
+// -1 when that row is past the end of the batch (evaluates on zeros, result ignored by callers).
+// Returns the value stack top in out[]; bit r of the return value is set when row r divided by 0.
+template <int DEPTH, int R>
+__device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog, const long long (&rows)[R],
+                                                 unsigned long long (&out)[R]) {
+  unsigned long long st[DEPTH][R];
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++)
+#pragma unroll
+    for (int r = 0; r < R; r++) st[d][r] = 0;
+  unsigned badmask = 0;
+  const int begin = ps.start[prog], end = ps.start[prog + 1];
+  for (int pc = begin; pc < end; ++pc) {
+    const int op = ps.insn[pc].op;
+    const int mode = ps.insn[pc].mode;
+    const int mt = ps.insn[pc].mtype;
+    const int dt = ps.insn[pc].dtype;
+    const int slot = ps.insn[pc].slot;
+    const unsigned long long imm = ps.insn[pc].imm;
+    if (op <= V_PUSH_IMM) {
+      // push
+#pragma unroll
+      for (int d = DEPTH - 1; d > 0; d--)
+#pragma unroll
+        for (int r = 0; r < R; r++) st[d][r] = st[d - 1][r];
+      if (op == V_PUSH_IMM) {
+#pragma unroll
+        for (int r = 0; r < R; r++) st[0][r] = imm;
+      } else {
+        const void* p = ps.cols[slot].ptr;
+        const int cdt = ps.cols[slot].dtype;
+#pragma unroll
+        for (int r = 0; r < R; r++) st[0][r] = rows[r] >= 0 ? load_elem(p, cdt, rows[r]) : 0ull;
+      }
+    } else if (op == V_CAST) {
+      const int src_dt = ps.insn[pc].aux;
+#pragma unroll
+      for (int r = 0; r < R; r++) st[0][r] = cast_value(st[0][r], mt, src_dt, dt);
+    } else {
+      unsigned long long rhs[R];
+      if (mode == RHS_IMM) {
+#pragma unroll
+        for (int r = 0; r < R; r++) rhs[r] = imm;
+      } else if (mode == RHS_COL) {
+        const void* p = ps.cols[slot].ptr;
+        const int cdt = ps.cols[slot].dtype;
+#pragma unroll
+        for (int r = 0; r < R; r++) rhs[r] = rows[r] >= 0 ? load_elem(p, cdt, rows[r]) : 0ull;
+      } else {
+        // pop: rhs = top, lhs = next; shift the stack down by one
+#pragma unroll
+        for (int r = 0; r < R; r++) rhs[r] = st[0][r];
+#pragma unroll
+        for (int d = 0; d < DEPTH - 1; d++)
+#pragma unroll
+          for (int r = 0; r < R; r++) st[d][r] = st[d + 1][r];
+      }
+      // The (machine type, op) dispatch is hoisted out of the per-row loop: it is warp-uniform and
+      // paid once per R rows.  A zero divisor sets the row's bit in badmask (arrow 0.12
+      // array_ops::divide returns ArrowError::DivideByZero for ints and floats alike).
+#define DF_ROWS(EXPR) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long a = st[0][r], b = rhs[r]; (void)a; (void)b; st[0][r] = (EXPR); }
+#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if ((COND) && rows[r] >= 0) badmask |= 1u << r; }
+      switch (mt) {
+        case MT_F64:
+          switch (op) {
+            case V_ADD: DF_ROWS(d2u(u2d(a) + u2d(b))) break;
+            case V_SUB: DF_ROWS(d2u(u2d(a) - u2d(b))) break;
+            case V_MUL: DF_ROWS(d2u(u2d(a) * u2d(b))) break;
+            case V_DIV: DF_DIVCHK(u2d(b) == 0.0) DF_ROWS(d2u(u2d(a) / u2d(b))) break;
+            case V_EQ: DF_ROWS((unsigned long long)(u2d(a) == u2d(b))) break;
+            case V_NE: DF_ROWS((unsigned long long)(u2d(a) != u2d(b))) break;
+            case V_LT: DF_ROWS((unsigned long long)(u2d(a) < u2d(b))) break;
+            case V_LE: DF_ROWS((unsigned long long)(u2d(a) <= u2d(b))) break;
+            case V_GT: DF_ROWS((unsigned long long)(u2d(a) > u2d(b))) break;
+            default: DF_ROWS((unsigned long long)(u2d(a) >= u2d(b))) break;
+          }
+          break;
+        case MT_F32:
+          switch (op) {
+            case V_ADD: DF_ROWS(f2u(u2f(a) + u2f(b))) break;
+            case V_SUB: DF_ROWS(f2u(u2f(a) - u2f(b))) break;
+            case V_MUL: DF_ROWS(f2u(u2f(a) * u2f(b))) break;
+            case V_DIV: DF_DIVCHK(u2f(b) == 0.0f) DF_ROWS(f2u(u2f(a) / u2f(b))) break;
+            case V_EQ: DF_ROWS((unsigned long long)(u2f(a) == u2f(b))) break;
+            case V_NE: DF_ROWS((unsigned long long)(u2f(a) != u2f(b))) break;
+            case V_LT: DF_ROWS((unsigned long long)(u2f(a) < u2f(b))) break;
+            case V_LE: DF_ROWS((unsigned long long)(u2f(a) <= u2f(b))) break;
+            case V_GT: DF_ROWS((unsigned long long)(u2f(a) > u2f(b))) break;
+            default: DF_ROWS((unsigned long long)(u2f(a) >= u2f(b))) break;
+          }
+          break;
+        case MT_I:
+          switch (op) {
+            case V_ADD: DF_ROWS(norm_int(a + b, dt)) break;
+            case V_SUB: DF_ROWS(norm_int(a - b, dt)) break;
+            case V_MUL: DF_ROWS(norm_int(a * b, dt)) break;
+            case V_DIV:
+              DF_DIVCHK(b == 0ull)
+              DF_ROWS(b == 0ull ? 0ull : ((long long)b == -1ll ? norm_int(0ull - a, dt) : norm_int((unsigned long long)((long long)a / (long long)b), dt)))
+              break;
+            case V_EQ: DF_ROWS((unsigned long long)(a == b)) break;
+            case V_NE: DF_ROWS((unsigned long long)(a != b)) break;
+            case V_LT: DF_ROWS((unsigned long long)((long long)a < (long long)b)) break;
+            case V_LE: DF_ROWS((unsigned long long)((long long)a <= (long long)b)) break;
+            case V_GT: DF_ROWS((unsigned long long)((long long)a > (long long)b)) break;
+            default: DF_ROWS((unsigned long long)((long long)a >= (long long)b)) break;
+          }
+          break;
+        case MT_U:
+          switch (op) {
+            case V_ADD: DF_ROWS(norm_int(a + b, dt)) break;
+            case V_SUB: DF_ROWS(norm_int(a - b, dt)) break;
+            case V_MUL: DF_ROWS(norm_int(a * b, dt)) break;
+            case V_DIV: DF_DIVCHK(b == 0ull) DF_ROWS(b == 0ull ? 0ull : a / b) break;
+            case V_EQ: DF_ROWS((unsigned long long)(a == b)) break;
+            case V_NE: DF_ROWS((unsigned long long)(a != b)) break;
+            case V_LT: DF_ROWS((unsigned long long)(a < b)) break;
+            case V_LE: DF_ROWS((unsigned long long)(a <= b)) break;
+            case V_GT: DF_ROWS((unsigned long long)(a > b)) break;
+            default: DF_ROWS((unsigned long long)(a >= b)) break;
+          }
+          break;
+        default:  // MT_BOOL
+          switch (op) {
+            case V_AND: DF_ROWS(a & b) break;
+            case V_OR: DF_ROWS(a | b) break;
+            case V_EQ: DF_ROWS((unsigned long long)(a == b)) break;
+            default: DF_ROWS((unsigned long long)(a != b)) break;
+          }
+          break;
+      }
+#undef DF_ROWS
+#undef DF_DIVCHK
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; r++) out[r] = st[0][r];
+  return badmask;
+}
+#endif  // __CUDACC__
+
+}  // namespace dfgpu

@@ -1,0 +1,295 @@
+// filter_project.cu — FilterRelation + ProjectRelation as ONE order-preserving stream-compaction
+// kernel (K1 predicate-eval + K2 filter-gather + K3 fused expr/project of SURVEY.md §2b).
+//
+// Reference path replaced (per batch): predicate closure -> BooleanArray (src/execution/filter.rs:50),
+// per-column builder gather of EVERY input column (filter.rs:55-57,79-110), then one closure pass
+// per projection expression (src/execution/projection.rs:49-50).  Here: one pass over the referenced
+// columns only; the predicate lives in registers as ballot masks, never in HBM; projected values are
+// computed in registers and written straight to their compacted position.
+//
+// Order preservation (filter.rs:86-90 appends in row order) = single-pass chained scan with
+// decoupled look-back across tiles; tiles are claimed through an atomic ticket so that a tile's
+// predecessors are always resident (forward progress without any grid-wide barrier).
+#include <memory>
+
+#include "expr_vm.cuh"
+
+namespace dfgpu {
+
+constexpr int FP_THREADS = 256;
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_R = 4;       // rows per interpreter pass (per thread)
+constexpr int FP_CHUNKS = 2;  // interpreter passes per tile
+constexpr int FP_ITEMS = FP_R * FP_CHUNKS;
+constexpr int FP_TILE = FP_THREADS * FP_ITEMS;
+
+struct FPParams {
+  ProgramSet ps;  // program 0 = predicate when has_pred, projections follow
+  void* out[kMaxProgs];
+  long long nrows;
+  int ntiles;
+  int has_pred;
+  int nproj;
+  unsigned long long* tile_status;  // [ntiles], zeroed per launch
+  unsigned* ticket;                 // zeroed per launch
+  unsigned long long* out_count;
+  unsigned* err_flag;
+};
+
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int DEPTH>
+__global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_constant__ FPParams p) {
+  __shared__ int s_tile;
+  __shared__ unsigned s_wcount[FP_ITEMS * FP_WARPS];
+  __shared__ unsigned s_woff[FP_ITEMS * FP_WARPS];
+  __shared__ unsigned long long s_prefix;
+  static_assert(FP_ITEMS * FP_WARPS == 64, "scan below assumes 64 (item,warp) counters = 2 per lane");
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (;;) {
+    if (tid == 0) s_tile = (int)atomicAdd(p.ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= p.ntiles) break;
+    const long long base = (long long)tile * FP_TILE;
+
+    // ---- phase 1: predicate -> per-thread flag bits (bit j = row base + j*THREADS + tid) ----
+    unsigned flags = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int c = 0; c < FP_CHUNKS; c++) {
+      long long rows[FP_R];
+#pragma unroll
+      for (int r = 0; r < FP_R; r++) {
+        long long row = base + (long long)(c * FP_R + r) * FP_THREADS + tid;
+        rows[r] = row < p.nrows ? row : -1;
+      }
+      if (p.has_pred) {
+        unsigned long long v[FP_R];
+        unsigned b = eval_program<DEPTH, FP_R>(p.ps, 0, rows, v);
+        bad = bad || (b != 0);
+#pragma unroll
+        for (int r = 0; r < FP_R; r++)
+          if (rows[r] >= 0 && (v[r] & 1ull)) flags |= 1u << (c * FP_R + r);
+      } else {
+#pragma unroll
+        for (int r = 0; r < FP_R; r++)
+          if (rows[r] >= 0) flags |= 1u << (c * FP_R + r);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FP_ITEMS; j++) {
+      unsigned b = __ballot_sync(0xffffffffu, (flags >> j) & 1u);
+      if (lane == 0) s_wcount[j * FP_WARPS + warp] = __popc(b);
+    }
+    __syncthreads();
+
+    // ---- warp 0: scan the 64 (item,warp) counts, then chain to the preceding tiles ----
+    if (warp == 0) {
+      unsigned c0 = s_wcount[2 * lane], c1 = s_wcount[2 * lane + 1];
+      unsigned incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      unsigned excl = incl - (c0 + c1);
+      s_woff[2 * lane] = excl;
+      s_woff[2 * lane + 1] = excl + c0;
+      const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+
+      unsigned long long prefix = 0;
+      if (!p.has_pred) {
+        prefix = (unsigned long long)base;  // nothing is dropped: positions are known without chaining
+      } else if (tile == 0) {
+        if (lane == 0) st_relaxed(&p.tile_status[0], ST_INCL | total);
+      } else {
+        if (lane == 0) st_relaxed(&p.tile_status[tile], ST_AGG | total);
+        long long look = (long long)tile - 1;
+        unsigned long long run = 0;
+        for (;;) {
+          const long long idx = look - lane;
+          unsigned long long s = idx >= 0 ? ld_relaxed(&p.tile_status[idx]) : ST_INCL;  // before tile 0: inclusive 0
+          while (__any_sync(0xffffffffu, (s >> 62) == 0)) {
+            if ((s >> 62) == 0) s = ld_relaxed(&p.tile_status[idx]);
+          }
+          const unsigned incl_mask = __ballot_sync(0xffffffffu, (s >> 62) == 2);
+          if (incl_mask) {
+            const int first = __ffs(incl_mask) - 1;  // nearest predecessor holding an inclusive prefix
+            run += warp_sum64(lane <= first ? (s & ST_MASK) : 0ull);
+            break;
+          }
+          run += warp_sum64(s & ST_MASK);
+          look -= 32;
+        }
+        prefix = run;
+        if (lane == 0) st_relaxed(&p.tile_status[tile], ST_INCL | (prefix + total));
+      }
+      if (lane == 0) {
+        s_prefix = prefix;
+        if (tile == p.ntiles - 1) *p.out_count = prefix + total;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase 2: evaluate the projections, write selected rows at their compacted position ----
+    const unsigned long long prefix = s_prefix;
+    for (int q = 0; q < p.nproj; q++) {
+      const int prog = q + p.has_pred;
+      const int odt = p.ps.out_dtype[prog];
+      void* o = p.out[q];
+#pragma unroll 1
+      for (int c = 0; c < FP_CHUNKS; c++) {
+        long long rows[FP_R];
+#pragma unroll
+        for (int r = 0; r < FP_R; r++) {
+          long long row = base + (long long)(c * FP_R + r) * FP_THREADS + tid;
+          rows[r] = row < p.nrows ? row : -1;
+        }
+        unsigned long long v[FP_R];
+        const unsigned b = eval_program<DEPTH, FP_R>(p.ps, prog, rows, v);
+#pragma unroll
+        for (int r = 0; r < FP_R; r++) {
+          const int j = c * FP_R + r;
+          const bool f = (flags >> j) & 1u;
+          const unsigned m = __ballot_sync(0xffffffffu, f);
+          if (f) {
+            const unsigned long long idx = prefix + s_woff[j * FP_WARPS + warp] + __popc(m & lt_mask);
+            store_elem(o, odt, (long long)idx, v[r]);
+            // DivideByZero only counts for rows that survive the filter: ProjectRelation runs on
+            // the filtered batch (src/execution/context.rs:140-161).
+            if ((b >> r) & 1u) bad = true;
+          }
+        }
+      }
+    }
+    if (bad) *p.err_flag = 1u;
+    __syncthreads();  // s_tile / s_wcount are reused by the next tile
+  }
+}
+
+template <int DEPTH>
+static void launch_fp(dfgpu_ctx* ctx, const FPParams& p) {
+  int per_sm = 0;
+  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_project<DEPTH>, FP_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)ctx->sm_count * per_sm;
+  if (grid > p.ntiles) grid = p.ntiles;
+  const int ps = ctx->prof_begin();
+  k_filter_project<DEPTH><<<(unsigned)grid, FP_THREADS, 0, ctx->stream>>>(p);
+  DF_CUDA(cudaGetLastError());
+  ctx->prof_end(ps);
+  ctx->launches++;
+}
+
+}  // namespace dfgpu
+
+using namespace dfgpu;
+
+extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_insn* pred, int pred_len,
+                                    const dfgpu_insn* const* proj, const int* proj_len, int nproj, dfgpu_result** out) {
+  return guarded([&] {
+    if (!ctx || !batch || !out) fail(DFGPU_ERR_GENERAL, "dfgpu_filter_project: null argument");
+    ctx->use();
+    ProgramBuilder pb(batch);
+    const int has_pred = pred_len > 0 ? 1 : 0;
+    if (has_pred) {
+      int pi = pb.add(pred, pred_len, "predicate");
+      if (pb.out_dtype(pi) != DFGPU_BOOL)  // filter.rs:64-66
+        fail(DFGPU_ERR_EXECUTION, "Filter expression did not evaluate to boolean");
+    }
+    // nproj == 0: FilterRelation alone emits every input column (filter.rs:55-57)
+    std::vector<dfgpu_insn> ident;
+    std::vector<const dfgpu_insn*> pptr;
+    std::vector<int> plen;
+    if (nproj == 0) {
+      ident.resize(batch->cols.size());
+      for (size_t i = 0; i < batch->cols.size(); i++) {
+        memset(&ident[i], 0, sizeof(dfgpu_insn));
+        ident[i].op = DFGPU_OP_COL;
+        ident[i].col = int(i);
+        ident[i].dtype = batch->cols[i].dtype;
+      }
+      for (size_t i = 0; i < batch->cols.size(); i++) {
+        pptr.push_back(&ident[i]);
+        plen.push_back(1);
+      }
+      nproj = int(batch->cols.size());
+      proj = pptr.data();
+      proj_len = plen.data();
+    }
+    for (int i = 0; i < nproj; i++) {
+      int pi = pb.add(proj[i], proj_len[i], "projection");
+      int dt = pb.out_dtype(pi);
+      if (!is_numeric(dt))
+        fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("filter/projection output of type ") + dtype_name(dt) +
+                                            " is not supported on the GPU path yet");
+    }
+    // columns referenced anywhere must be null-free and fixed width for now
+    FPParams p;
+    pb.finish(&p.ps);
+    for (int s = 0; s < p.ps.ncols; s++) {
+      if (!is_numeric(p.ps.cols[s].dtype))
+        fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("expressions over ") + dtype_name(p.ps.cols[s].dtype) + " columns are not supported on the GPU path yet");
+    }
+    for (const auto& c : batch->cols)
+      if (c.null_count > 0) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
+    if (p.ps.max_depth > 8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression too deep (register stack depth > 8)");
+
+    auto res = std::make_unique<dfgpu_result>();
+    res->ctx = ctx;
+    const long long n = batch->nrows;
+    for (int i = 0; i < nproj; i++) {
+      DevColumn c;
+      c.dtype = pb.out_dtype(i + has_pred);
+      c.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(c.dtype));
+      c.values = ctx->alloc(c.values_bytes);
+      res->cols.push_back(c);
+    }
+    if (n == 0) {
+      res->nrows = 0;
+      *out = res.release();
+      return;
+    }
+    p.nrows = n;
+    p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
+    p.has_pred = has_pred;
+    p.nproj = nproj;
+    for (int i = 0; i < nproj; i++) p.out[i] = res->cols[size_t(i)].values;
+    unsigned long long* status = (unsigned long long*)ctx->alloc(size_t(p.ntiles) * 8);
+    DF_CUDA(cudaMemsetAsync(status, 0, size_t(p.ntiles) * 8, ctx->stream));
+    DF_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 32, ctx->stream));
+    p.tile_status = status;
+    p.out_count = ctx->d_scratch + 0;
+    p.ticket = (unsigned*)(ctx->d_scratch + 1);
+    p.err_flag = (unsigned*)(ctx->d_scratch + 2);
+    const int d = p.ps.max_depth;
+    if (d <= 1) launch_fp<1>(ctx, p);
+    else if (d <= 2) launch_fp<2>(ctx, p);
+    else if (d <= 4) launch_fp<4>(ctx, p);
+    else launch_fp<8>(ctx, p);
+    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->free(status);
+    if ((unsigned)ctx->h_scratch[2] != 0) fail(DFGPU_ERR_ARROW, "DivideByZero");
+    res->nrows = (int64_t)ctx->h_scratch[0];
+    *out = res.release();
+  });
+}

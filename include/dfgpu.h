@@ -152,6 +152,12 @@ int dfgpu_timer_stop(dfgpu_ctx* ctx, float* ms);
 int dfgpu_flush_l2(dfgpu_ctx* ctx);
 /* Counters: number of engine kernels launched on this ctx since init. */
 int dfgpu_kernel_launches(const dfgpu_ctx* ctx, int64_t* out);
+/* Per-kernel device timing of the dominant (scan) kernels: CUDA events recorded on the ctx stream
+ * immediately around each launch of the filter/project, hash-aggregate and reduce kernels.
+ * enable(1) starts a fresh accumulation; get() synchronises and returns the summed kernel time and
+ * the number of timed launches since enable. */
+int dfgpu_profile_enable(dfgpu_ctx* ctx, int on);
+int dfgpu_profile_get(dfgpu_ctx* ctx, double* kernel_ms, int64_t* launches);
 
 /* ---- batches: the RecordBatch handed to Relation::next's consumer (src/execution/relation.rs:27-32) ---- */
 /* Copy the Arrow buffers of one RecordBatch into HBM (one cudaMemcpyAsync per buffer; pageable
