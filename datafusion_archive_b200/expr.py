@@ -48,11 +48,12 @@ class Column(Expr):
         self.index = index
 
     def get_type(self, schema):
-        return schema[self.index]
+        return schema[self.index] if 0 <= self.index < len(schema) else 0
 
     def _emit(self, schema, out):
         i = A.Insn()
-        i.op, i.col, i.dtype = A.OP_COL, self.index, schema[self.index]
+        # an out-of-range index is passed through: the engine reports InvalidColumn
+        i.op, i.col, i.dtype = A.OP_COL, self.index, (schema[self.index] if 0 <= self.index < len(schema) else 0)
         out.append(i)
 
     def __repr__(self):
