@@ -176,11 +176,14 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     if (tid == 0) s_full = (long long)__ldcg(&p.counters[0]) >= p.max_groups;
     __syncthreads();
     const bool full = s_full != 0;
-    long long rows[AG_R];
+    GlobalRows<AG_R> src;
+    src.valid = 0;
+    long long (&rows)[AG_R] = src.rows;
 #pragma unroll
     for (int r = 0; r < AG_R; r++) {
       const long long i = tb + (long long)r * AG_THREADS + tid;
       rows[r] = i < n ? (p.row_list ? (long long)p.row_list[i] : i) : -1;
+      if (i < n) src.valid |= 1u << r;
     }
     // group key: one packed 64-bit word (GroupByScalar vector of aggregate.rs:807-852)
     unsigned long long key[AG_R];
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     for (int r = 0; r < AG_R; r++) key[r] = 0;
     for (int k = 0; k < p.nkeys; k++) {
       unsigned long long v[AG_R];
-      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, k, rows, v);
+      const unsigned b = eval_program<DEPTH, AG_R, false>(p.ps, k, src, v);
       bad = bad || (b != 0);
 #pragma unroll
       for (int r = 0; r < AG_R; r++) key[r] |= (v[r] & p.key_mask[k]) << p.key_shift[k];
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     // accumulators (update_accumulators, aggregate.rs:548-612): argument evaluated once per row
     for (int a = 0; a < p.naggs; a++) {
       unsigned long long v[AG_R];
-      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, p.nkeys + a, rows, v);
+      const unsigned b = eval_program<DEPTH, AG_R, false>(p.ps, p.nkeys + a, src, v);
       const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
       unsigned long long* col = p.vals + (long long)a * stride;
 #pragma unroll
@@ -249,15 +252,18 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
   for (int a = 0; a < p.naggs; a++) s_acc[a][tid] = agg_identity(p.aggs[a].func);
   bool bad = false;
   for (long long tb = (long long)blockIdx.x * AG_TILE; tb < p.nrows; tb += (long long)gridDim.x * AG_TILE) {
-    long long rows[AG_R];
+    GlobalRows<AG_R> src;
+    src.valid = 0;
+    long long (&rows)[AG_R] = src.rows;
 #pragma unroll
     for (int r = 0; r < AG_R; r++) {
       const long long i = tb + (long long)r * AG_THREADS + tid;
       rows[r] = i < p.nrows ? i : -1;
+      if (i < p.nrows) src.valid |= 1u << r;
     }
     for (int a = 0; a < p.naggs; a++) {
       unsigned long long v[AG_R];
-      const unsigned b = eval_program<DEPTH, AG_R>(p.ps, a, rows, v);
+      const unsigned b = eval_program<DEPTH, AG_R, false>(p.ps, a, src, v);
       bad = bad || (b != 0);
       const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
       unsigned long long acc = s_acc[a][tid];

@@ -168,6 +168,7 @@ extern "C" int dfgpu_init(int device, dfgpu_ctx** out) {
       fail(DFGPU_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major * 10 + prop.minor) +
                                "; this library is built for sm_100a (B200) only");
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("DFGPU_FP_KERNEL")) ctx->force_direct_kernel = std::string(e) == "direct";
     DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     DF_CUDA(cudaEventCreate(&ctx->ev_start));
     DF_CUDA(cudaEventCreate(&ctx->ev_stop));

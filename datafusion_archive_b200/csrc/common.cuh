@@ -65,6 +65,7 @@ struct dfgpu_ctx {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   int64_t launches = 0;
+  bool force_direct_kernel = false;  // DFGPU_FP_KERNEL=direct: bypass the TMA pipeline (A/B testing)
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   // device scratch shared by operators (error flags, counters); 64 x u64

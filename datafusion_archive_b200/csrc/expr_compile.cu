@@ -238,6 +238,11 @@ void ProgramBuilder::finish(ProgramSet* out) const {
     out->out_dtype[i] = uint8_t(progs_[i].out_dtype);
     if (progs_[i].max_depth > maxd) maxd = progs_[i].max_depth;
   }
+  out->f64_only = 1;
+  for (int i = 0; i < pc; i++) {
+    const DevInsn& di = out->insn[i];
+    if (di.op == V_CAST || !(di.mtype == MT_F64 || di.mtype == MT_BOOL)) out->f64_only = 0;
+  }
   out->start[progs_.size()] = uint8_t(pc);
   out->nprog = int(progs_.size());
   out->ncols = int(slots_.size());

@@ -50,6 +50,7 @@ struct ProgramSet {
   int nprog;
   int ncols;
   int max_depth;
+  int f64_only;  // every operand Float64/Boolean and no CAST: the lean evaluator applies
 };
 
 // ---- host side ----------------------------------------------------------------------------
@@ -115,6 +116,42 @@ __device__ __forceinline__ unsigned long long load_elem(const void* p, int dtype
   }
 }
 
+// same, through a generic pointer (shared-memory staged tiles)
+__device__ __forceinline__ unsigned long long load_elem_generic(const void* p, int dtype, int idx) {
+  switch (dtype) {
+    case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64: return ((const unsigned long long*)p)[idx];
+    case DFGPU_FLOAT32: case DFGPU_UINT32: return (unsigned long long)((const unsigned*)p)[idx];
+    case DFGPU_INT32: return (unsigned long long)(long long)((const int*)p)[idx];
+    case DFGPU_INT16: return (unsigned long long)(long long)((const short*)p)[idx];
+    case DFGPU_UINT16: return (unsigned long long)((const unsigned short*)p)[idx];
+    case DFGPU_INT8: return (unsigned long long)(long long)((const signed char*)p)[idx];
+    case DFGPU_UINT8: return (unsigned long long)((const unsigned char*)p)[idx];
+    default: return 0;
+  }
+}
+
+// Operand sources for the evaluator.  GlobalRows: R arbitrary row indices straight from HBM
+// (-1 = past the end).  StagedTile: rows lrow0 + r*32 of a tile staged in shared memory, columns
+// laid out back to back at col_off[slot]; validity comes from `valid` (bit r).
+template <int R>
+struct GlobalRows {
+  long long rows[R];
+  unsigned valid;
+  __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
+    return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
+  }
+};
+template <int R>
+struct StagedTile {
+  const unsigned char* stage;
+  const int* col_off;
+  int lrow0;
+  unsigned valid;
+  __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
+    return load_elem_generic(stage + col_off[slot], ps.cols[slot].dtype, lrow0 + r * 32);
+  }
+};
+
 __device__ __forceinline__ void store_elem(void* p, int dtype, long long idx, unsigned long long v) {
   switch (dtype) {
     case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64: ((unsigned long long*)p)[idx] = v; break;
@@ -176,11 +213,12 @@ __device__ __forceinline__ unsigned long long cast_value(unsigned long long v, i
   return norm_int(v, dst_dt);  // int -> int: truncate / extend (value already sign/zero extended)
 }
 
-// Evaluate program [begin,end) of `ps` for R rows.  `rows[r]` is the row index of lane-row r, or
-// -1 when that row is past the end of the batch (evaluates on zeros, result ignored by callers).
-// Returns the value stack top in out[]; bit r of the return value is set when row r divided by 0.
-template <int DEPTH, int R>
-__device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog, const long long (&rows)[R],
+// Evaluate program `prog` of `ps` for the R rows described by `src` (GlobalRows / StagedTile).
+// Returns the value stack top in out[]; bit r of the return value is set when valid row r divided
+// by zero.  With F64ONLY every operand is Float64/Boolean (checked on the host): the machine-type
+// dispatch disappears and only the warp-uniform opcode switch is left.
+template <int DEPTH, int R, bool F64ONLY, class Src>
+__device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog, const Src& src,
                                                  unsigned long long (&out)[R]) {
   unsigned long long st[DEPTH][R];
 #pragma unroll
@@ -206,10 +244,8 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
 #pragma unroll
         for (int r = 0; r < R; r++) st[0][r] = imm;
       } else {
-        const void* p = ps.cols[slot].ptr;
-        const int cdt = ps.cols[slot].dtype;
 #pragma unroll
-        for (int r = 0; r < R; r++) st[0][r] = rows[r] >= 0 ? load_elem(p, cdt, rows[r]) : 0ull;
+        for (int r = 0; r < R; r++) st[0][r] = src.load(ps, slot, r);
       }
     } else if (op == V_CAST) {
       const int src_dt = ps.insn[pc].aux;
@@ -221,10 +257,8 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
 #pragma unroll
         for (int r = 0; r < R; r++) rhs[r] = imm;
       } else if (mode == RHS_COL) {
-        const void* p = ps.cols[slot].ptr;
-        const int cdt = ps.cols[slot].dtype;
 #pragma unroll
-        for (int r = 0; r < R; r++) rhs[r] = rows[r] >= 0 ? load_elem(p, cdt, rows[r]) : 0ull;
+        for (int r = 0; r < R; r++) rhs[r] = src.load(ps, slot, r);
       } else {
         // pop: rhs = top, lhs = next; shift the stack down by one
 #pragma unroll
@@ -238,8 +272,8 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
       // paid once per R rows.  A zero divisor sets the row's bit in badmask (arrow 0.12
       // array_ops::divide returns ArrowError::DivideByZero for ints and floats alike).
 #define DF_ROWS(EXPR) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long a = st[0][r], b = rhs[r]; (void)a; (void)b; st[0][r] = (EXPR); }
-#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if ((COND) && rows[r] >= 0) badmask |= 1u << r; }
-      switch (mt) {
+#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if (COND) badmask |= 1u << r; }
+      switch (F64ONLY ? (op >= V_AND ? (int)MT_BOOL : (int)MT_F64) : mt) {
         case MT_F64:
           switch (op) {
             case V_ADD: DF_ROWS(d2u(u2d(a) + u2d(b))) break;
@@ -314,7 +348,7 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
   }
 #pragma unroll
   for (int r = 0; r < R; r++) out[r] = st[0][r];
-  return badmask;
+  return badmask & src.valid;
 }
 #endif  // __CUDACC__
 

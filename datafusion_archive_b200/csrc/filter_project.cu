@@ -12,45 +12,9 @@
 // predecessors are always resident (forward progress without any grid-wide barrier).
 #include <memory>
 
-#include "expr_vm.cuh"
+#include "filter_project.cuh"
 
 namespace dfgpu {
-
-constexpr int FP_THREADS = 256;
-constexpr int FP_WARPS = FP_THREADS / 32;
-constexpr int FP_R = 4;       // rows per interpreter pass (per thread)
-constexpr int FP_CHUNKS = 2;  // interpreter passes per tile
-constexpr int FP_ITEMS = FP_R * FP_CHUNKS;
-constexpr int FP_TILE = FP_THREADS * FP_ITEMS;
-
-struct FPParams {
-  ProgramSet ps;  // program 0 = predicate when has_pred, projections follow
-  void* out[kMaxProgs];
-  long long nrows;
-  int ntiles;
-  int has_pred;
-  int nproj;
-  unsigned long long* tile_status;  // [ntiles], zeroed per launch
-  unsigned* ticket;                 // zeroed per launch
-  unsigned long long* out_count;
-  unsigned* err_flag;
-};
-
-constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_MASK = (1ull << 62) - 1;
-
-__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
 
 template <int DEPTH>
 __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_constant__ FPParams p) {
@@ -75,23 +39,23 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
     bool bad = false;
 #pragma unroll 1
     for (int c = 0; c < FP_CHUNKS; c++) {
-      long long rows[FP_R];
+      GlobalRows<FP_R> src;
+      src.valid = 0;
 #pragma unroll
       for (int r = 0; r < FP_R; r++) {
         long long row = base + (long long)(c * FP_R + r) * FP_THREADS + tid;
-        rows[r] = row < p.nrows ? row : -1;
+        src.rows[r] = row < p.nrows ? row : -1;
+        if (row < p.nrows) src.valid |= 1u << r;
       }
       if (p.has_pred) {
         unsigned long long v[FP_R];
-        unsigned b = eval_program<DEPTH, FP_R>(p.ps, 0, rows, v);
+        unsigned b = eval_program<DEPTH, FP_R, false>(p.ps, 0, src, v);
         bad = bad || (b != 0);
 #pragma unroll
         for (int r = 0; r < FP_R; r++)
-          if (rows[r] >= 0 && (v[r] & 1ull)) flags |= 1u << (c * FP_R + r);
+          if (((src.valid >> r) & 1u) && (v[r] & 1ull)) flags |= 1u << (c * FP_R + r);
       } else {
-#pragma unroll
-        for (int r = 0; r < FP_R; r++)
-          if (rows[r] >= 0) flags |= 1u << (c * FP_R + r);
+        flags |= src.valid << (c * FP_R);
       }
     }
 #pragma unroll
@@ -157,14 +121,16 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
       void* o = p.out[q];
 #pragma unroll 1
       for (int c = 0; c < FP_CHUNKS; c++) {
-        long long rows[FP_R];
+        GlobalRows<FP_R> src;
+        src.valid = 0;
 #pragma unroll
         for (int r = 0; r < FP_R; r++) {
           long long row = base + (long long)(c * FP_R + r) * FP_THREADS + tid;
-          rows[r] = row < p.nrows ? row : -1;
+          src.rows[r] = row < p.nrows ? row : -1;
+          if (row < p.nrows) src.valid |= 1u << r;
         }
         unsigned long long v[FP_R];
-        const unsigned b = eval_program<DEPTH, FP_R>(p.ps, prog, rows, v);
+        const unsigned b = eval_program<DEPTH, FP_R, false>(p.ps, prog, src, v);
 #pragma unroll
         for (int r = 0; r < FP_R; r++) {
           const int j = c * FP_R + r;
@@ -269,22 +235,53 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       return;
     }
     p.nrows = n;
-    p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
     p.has_pred = has_pred;
     p.nproj = nproj;
     for (int i = 0; i < nproj; i++) p.out[i] = res->cols[size_t(i)].values;
-    unsigned long long* status = (unsigned long long*)ctx->alloc(size_t(p.ntiles) * 8);
-    DF_CUDA(cudaMemsetAsync(status, 0, size_t(p.ntiles) * 8, ctx->stream));
+    // tile_status is sized for the smallest tile either kernel uses (1024 rows)
+    const size_t max_tiles = size_t((n + 1023) / 1024) + 1;
+    unsigned long long* status = (unsigned long long*)ctx->alloc(max_tiles * 8);
+    DF_CUDA(cudaMemsetAsync(status, 0, max_tiles * 8, ctx->stream));
     DF_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 32, ctx->stream));
     p.tile_status = status;
     p.out_count = ctx->d_scratch + 0;
     p.ticket = (unsigned*)(ctx->d_scratch + 1);
     p.err_flag = (unsigned*)(ctx->d_scratch + 2);
-    const int d = p.ps.max_depth;
-    if (d <= 1) launch_fp<1>(ctx, p);
-    else if (d <= 2) launch_fp<2>(ctx, p);
-    else if (d <= 4) launch_fp<4>(ctx, p);
-    else launch_fp<8>(ctx, p);
+    // fast shapes (see FPParams): straight from the lowered bytecode
+    auto fast_of = [&](int prog, bool is_pred) {
+      FastOp f;
+      memset(&f, 0, sizeof(f));
+      const int b = p.ps.start[prog], e = p.ps.start[prog + 1];
+      const DevInsn* in = &p.ps.insn[b];
+      auto f64col = [&](int slot) { return p.ps.cols[slot].dtype == DFGPU_FLOAT64; };
+      if (in[0].op != V_PUSH_COL || !f64col(in[0].slot)) return f;
+      if (e - b == 1 && !is_pred) {
+        f.kind = 1;
+        f.a = in[0].slot;
+        return f;
+      }
+      if (e - b != 2 || in[1].mtype != MT_F64 || in[1].mode == RHS_STACK) return f;
+      const bool cmp = in[1].op >= V_EQ && in[1].op <= V_GE, arith = in[1].op >= V_ADD && in[1].op <= V_DIV;
+      if (is_pred ? !cmp : !arith) return f;
+      if (in[1].mode == RHS_COL && !f64col(in[1].slot)) return f;
+      f.kind = in[1].mode == RHS_COL ? 2 : 3;
+      f.op = in[1].op;
+      f.a = in[0].slot;
+      f.b = in[1].slot;
+      memcpy(&f.imm, &in[1].imm, 8);
+      return f;
+    };
+    memset(&p.pred_fast, 0, sizeof(p.pred_fast));
+    if (has_pred) p.pred_fast = fast_of(0, true);
+    for (int i = 0; i < nproj; i++) p.proj_fast[i] = fast_of(i + has_pred, false);
+    if (ctx->force_direct_kernel || !launch_fp_tma(ctx, p)) {
+      p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
+      const int d = p.ps.max_depth;
+      if (d <= 1) launch_fp<1>(ctx, p);
+      else if (d <= 2) launch_fp<2>(ctx, p);
+      else if (d <= 4) launch_fp<4>(ctx, p);
+      else launch_fp<8>(ctx, p);
+    }
     DF_CUDA(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, ctx->stream));
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->free(status);

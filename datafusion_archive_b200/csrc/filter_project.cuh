@@ -1,0 +1,67 @@
+// filter_project.cuh — parameter block and chained-scan helpers shared by the two filter/project
+// kernels (filter_project.cu: direct-load kernel; filter_project_tma.cu: TMA-staged pipeline).
+#pragma once
+#include "expr_vm.cuh"
+
+namespace dfgpu {
+
+constexpr int FP_THREADS = 256;
+constexpr int FP_WARPS = FP_THREADS / 32;
+constexpr int FP_R = 4;       // rows per interpreter pass (per thread)
+constexpr int FP_CHUNKS = 2;  // interpreter passes per tile
+constexpr int FP_ITEMS = FP_R * FP_CHUNKS;
+constexpr int FP_TILE = FP_THREADS * FP_ITEMS;
+
+struct FastOp {
+  int kind;  // 0 = use the interpreter, 1 = copy column a, 2 = a op column b, 3 = a op imm
+  int op;    // VOp
+  int a, b;  // column slots
+  double imm;
+};
+
+struct FPParams {
+  ProgramSet ps;  // program 0 = predicate when has_pred, projections follow
+  void* out[kMaxProgs];
+  long long nrows;
+  int ntiles;
+  int has_pred;
+  int nproj;
+  unsigned long long* tile_status;  // [ntiles], zeroed per launch
+  unsigned* ticket;                 // zeroed per launch
+  unsigned long long* out_count;
+  unsigned* err_flag;
+  // TMA-staged kernel only: layout of one shared-memory stage (all referenced columns of a tile)
+  int col_off[kMaxCols];  // byte offset of column slot s inside a stage
+  int col_w[kMaxCols];    // element width of column slot s
+  int stage_bytes;
+  int nstages;
+  // "fast shapes": single-operation Float64 programs are recognised on the host and executed by
+  // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).
+  //   predicate : COL cmp COL | COL cmp IMM
+  //   projection: COL | COL op COL | COL op IMM          (op in + - * /)
+  FastOp pred_fast;
+  FastOp proj_fast[kMaxProgs];
+};
+
+constexpr unsigned long long ST_AGG = 1ull << 62, ST_INCL = 2ull << 62, ST_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long warp_sum64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+
+// filter_project_tma.cu: persistent warp-specialised kernel fed by cp.async.bulk (TMA) through a
+// shared-memory ring.  Returns false when the shape does not fit it (caller uses the direct kernel).
+bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p);
+
+}  // namespace dfgpu

@@ -22,7 +22,8 @@ class DfGpuError(Exception):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdfgpu.so")
+    # DFGPU_LIB: A/B-test another build of the same ABI (profiling experiments only)
+    return os.environ.get("DFGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdfgpu.so")
 
 
 def build(force=False):
@@ -131,7 +132,8 @@ class Result:
 
     def free(self):
         if self.h:
-            check(lib().dfgpu_result_free(self.h))
+            if self.ctx.h:  # after ctx.close() the device memory is gone with the context
+                check(lib().dfgpu_result_free(self.h))
             self.h = None
 
     def __del__(self):
@@ -180,7 +182,8 @@ class Batch:
 
     def free(self):
         if self.h:
-            check(lib().dfgpu_batch_free(self.h))
+            if self.ctx.h:
+                check(lib().dfgpu_batch_free(self.h))
             self.h = None
 
     def __del__(self):

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Short driver for ncu captures: runs each hot-path operator a few times on BASELINE-sized inputs.
+  ncu --set full --clock-control none --import-source on -k regex:k_filter_project -s 2 -c 1 -o gpurun_out/fp python profiles/run_kernels.py c2
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from datafusion_archive_b200 import engine, workloads  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+ctx = engine.GpuContext(0)
+if which in ("c2", "c3"):
+    arrays, pred, proj = (workloads.c2 if which == "c2" else workloads.c3)(n)
+    b = ctx.upload(arrays)
+    for _ in range(reps):
+        r = ctx.filter_project(b, pred, proj)
+        print(which, "rows out", r.nrows)
+        r.free()
+else:
+    arrays, keys, aggs, _ = (workloads.c4 if which == "c4" else workloads.c5)(n)
+    b = ctx.upload(arrays)
+    for _ in range(reps):
+        r = ctx.aggregate(b, keys, aggs)
+        print(which, "groups", r.nrows)
+        r.free()
+b.free()
+ctx.close()
