@@ -162,6 +162,15 @@ __device__ __forceinline__ void store_elem(void* p, int dtype, long long idx, un
   }
 }
 
+__device__ __forceinline__ int dtype_width_dev(int dtype) {
+  switch (dtype) {
+    case DFGPU_INT8: case DFGPU_UINT8: return 1;
+    case DFGPU_INT16: case DFGPU_UINT16: return 2;
+    case DFGPU_INT32: case DFGPU_UINT32: case DFGPU_FLOAT32: return 4;
+    default: return 8;
+  }
+}
+
 // Rust `as` (saturating float->int, NaN -> 0; wrapping int->int; nearest int->float)
 __device__ __forceinline__ unsigned long long cast_value(unsigned long long v, int src_mt, int src_dt, int dst_dt) {
   // to floats

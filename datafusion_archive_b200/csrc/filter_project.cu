@@ -286,7 +286,7 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->free(status);
     if ((unsigned)ctx->h_scratch[2] != 0) fail(DFGPU_ERR_ARROW, "DivideByZero");
-    res->nrows = (int64_t)ctx->h_scratch[0];
+    res->nrows = has_pred ? (int64_t)ctx->h_scratch[0] : n;
     *out = res.release();
   });
 }

@@ -30,11 +30,14 @@ struct FPParams {
   unsigned* ticket;                 // zeroed per launch
   unsigned long long* out_count;
   unsigned* err_flag;
-  // TMA-staged kernel only: layout of one shared-memory stage (all referenced columns of a tile)
-  int col_off[kMaxCols];  // byte offset of column slot s inside a stage
-  int col_w[kMaxCols];    // element width of column slot s
-  int stage_bytes;
-  int nstages;
+  // TMA-staged kernel only: layout of the two shared-memory rings.  Ring A stages hold the column
+  // slices the predicate reads, ring B stages the slices the projections read (-1 = not in ring).
+  int col_offA[kMaxCols];
+  int col_offB[kMaxCols];
+  int col_w[kMaxCols];  // element width of column slot s
+  int stage_bytesA, stage_bytesB;
+  int nstagesA, nstagesB;
+  int lag;  // tiles between the predicate pass and the projection pass
   // "fast shapes": single-operation Float64 programs are recognised on the host and executed by
   // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).
   //   predicate : COL cmp COL | COL cmp IMM

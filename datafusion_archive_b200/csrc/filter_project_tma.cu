@@ -1,37 +1,48 @@
 // filter_project_tma.cu — the production filter+project kernel: persistent, warp-specialised,
-// fed by the TMA engine.
+// fed by the TMA engine, with the predicate running far ahead of the projection.
 //
-//   producer warp : one elected lane issues cp.async.bulk (SASS UBLKCP) copies of the next tiles'
-//                   column slices HBM -> shared memory into a ring of stages, completion tracked by
-//                   mbarrier transaction counts (no registers, no LSU instructions on the load path)
-//   16 consumer   : evaluate the predicate over the staged tile (expression VM, K rows per lane),
-//   warps           keep the mask in registers (ballots), later evaluate the projections from the
-//                   same staged data and store selected rows at their compacted global position
-//   scan warp     : turns the 16 per-warp counts of a tile into global output offsets
+// Roles inside one CTA (one CTA per SM, cooperative launch, tiles assigned round-robin: in "wave"
+// `it` CTA c owns tile it*G + c):
 //
-// Tiles are assigned round-robin: in "wave" `it` CTA c owns tile it*G + c (G = gridDim.x = one
-// CTA per SM, all co-resident: cooperative launch).  A chained look-back would serialise on the
-// previous tile's owner once per tile, i.e. one L2 round trip of latency per tile per CTA, which
-// is longer than the tile's HBM time.  Instead every scan warp publishes its tile's count and then
-// GATHERS the counts of all G tiles of its wave in one batch of parallel loads: its own offset is
-// base + sum(counts of lower CTAs), and base advances by the wave total — computed redundantly by
-// every CTA, so no value is ever forwarded from one wave to the next through memory.
+//   producer A (1 warp) : one elected lane streams the PREDICATE columns of tile it into ring A with
+//                         cp.async.bulk (SASS UBLKCP), completion tracked by mbarrier tx counts
+//   producer B (1 warp) : streams the PROJECTION columns of tile it-LAG into ring B the same way —
+//                         a re-read of bytes fetched LAG tiles earlier, served by the 126 MB L2
+//   16 consumer warps   : phase 1 = predicate of tile it over ring A -> K flag bits per lane, kept in
+//                         a 64-bit shift register; phase 2 = projections of tile it-LAG over ring B,
+//                         selected rows stored at their compacted global position
+//   4 scan warps        : turn the per-warp counts of a tile into global output offsets, 4 waves per
+//                         warp at a time (16 cross-CTA gathers in flight per SM)
 //
-// Consumers run the predicate TM_LAG tiles ahead of the projections, so the gather latency of a
-// wave is hidden behind useful work; nothing in the CTA executes __syncthreads in the steady state
-// (all hand-offs are mbarriers).
+// Why the lag: order-preserving compaction needs, per tile, the number of selected rows in ALL
+// earlier tiles.  Under a bandwidth-saturating stream every dependent global round trip costs
+// microseconds, far longer than a tile's HBM time (~0.5 us), and a tile cannot wait in shared
+// memory that long (bandwidth x latency exceeds the SM's storage).  So the predicate pass, which
+// only produces 1 bit per row, runs LAG tiles ahead; by the time the projection pass reaches a
+// tile its offset has long been resolved, and the tile's bytes come back from L2, not HBM.
 //
+// Offsets: every scan warp publishes its tile's count, then GATHERS the counts of all G tiles of
+// its wave with one batch of parallel loads: offset = base + sum(counts of lower CTAs); base
+// advances by the wave total, computed redundantly by every CTA (nothing is forwarded between
+// waves through memory).  The 4 scan warps take waves round-robin so 4 gathers are in flight; the
+// running base is handed from wave to wave through shared memory.
+//
+// Nothing in the CTA executes __syncthreads in the steady state; all hand-offs are mbarriers.
 // Reference path replaced: src/execution/filter.rs:46-110 + src/execution/projection.rs:46-66.
 #include "filter_project.cuh"
 
 namespace dfgpu {
 
-constexpr int TM_CWARPS = 16;                     // consumer warps
-constexpr int TM_THREADS = (TM_CWARPS + 2) * 32;  // + producer warp + scan warp
+constexpr int TM_CWARPS = 16;  // consumer warps
+constexpr int TM_SWARPS = 4;   // scan warps
+constexpr int TM_BATCH = 4;    // waves per scan-warp batch
+constexpr int TM_WARPS = TM_CWARPS + 2 + TM_SWARPS;
+constexpr int TM_THREADS = TM_WARPS * 32;
 constexpr int TM_MAX_STAGES = 8;
-constexpr int TM_LAG = 2;    // predicate runs this many tiles ahead of the projection
-constexpr int TM_RING = 4;   // slots of the count/offset hand-off rings (> TM_LAG + 1)
-constexpr int TM_MAX_GRID = 256;
+constexpr int TM_RING = 32;       // slots of the count/offset hand-off rings (> max lag + 1)
+constexpr int TM_MAX_LAG = 16;
+constexpr int TM_MAX_GRID = 160;  // CTAs (= SMs) the wave gather is written for (B200: 148)
+constexpr int TM_HDR_BYTES = 8192;
 constexpr int TM_SMEM_BUDGET = 200 * 1024;
 
 // ---- mbarrier / bulk-copy PTX ----------------------------------------------------------------
@@ -50,11 +61,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "{\n"
       ".reg .pred P1;\n"
       "WAIT_LOOP:\n"
-#ifdef DF_TRYWAIT_HINT
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, " DF_TRYWAIT_HINT ";\n"
-#else
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-#endif
       "@P1 bra DONE;\n"
       "bra WAIT_LOOP;\n"
       "DONE:\n"
@@ -69,151 +76,214 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 
 struct TmaShared {
-  unsigned long long full[TM_MAX_STAGES];   // producer -> consumers: stage holds the tile
-  unsigned long long empty[TM_MAX_STAGES];  // consumers -> producer: stage may be overwritten
-  unsigned long long cnt_ready[TM_RING];    // consumers -> scan warp: per-warp counts of a tile are in s_cnt
-  unsigned long long pfx_ready[TM_RING];    // scan warp -> consumers: global offsets of a tile are in s_off
-  unsigned s_cnt[TM_RING][TM_CWARPS];
+  unsigned long long fullA[TM_MAX_STAGES], emptyA[TM_MAX_STAGES];  // ring A (predicate columns)
+  unsigned long long fullB[TM_MAX_STAGES], emptyB[TM_MAX_STAGES];  // ring B (projection columns)
+  unsigned long long cnt_ready[TM_RING];   // consumers -> scan warp: per-warp counts of a tile are in s_cnt
+  unsigned long long pfx_ready[TM_RING];   // scan warp -> consumers: global offsets of a tile are in s_off
+  unsigned long long base_ready[TM_RING];  // scan warp of wave it-1 -> scan warp of wave it
+  unsigned long long s_base[TM_RING];
   unsigned long long s_off[TM_RING][TM_CWARPS];
+  unsigned s_cnt[TM_RING][TM_CWARPS];
 };
+static_assert(sizeof(TmaShared) <= TM_HDR_BYTES, "shared header too large");
+
+// One producer warp: stream the `ncols` columns listed in `slots` of every tile this CTA owns into
+// a ring of S stages.
+__device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, const int* col_off, unsigned char* ring, int S,
+                                              int stage_bytes, unsigned long long* full, unsigned long long* empty, int lane) {
+  int s = 0;
+  unsigned ph = 1;  // first pass over the ring returns immediately
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    mbar_wait(&empty[s], ph);
+    unsigned char* dst = ring + (size_t)s * stage_bytes;
+    const long long row0 = (long long)tile * tile_rows;
+    const long long left = p.nrows - row0;
+    if (left >= tile_rows) {
+      if (lane == 0) {
+        unsigned total = 0;
+        for (int c = 0; c < p.ps.ncols; c++)
+          if (col_off[c] >= 0) total += (unsigned)(tile_rows * p.col_w[c]);
+        mbar_arrive_expect_tx(&full[s], total);
+        for (int c = 0; c < p.ps.ncols; c++)
+          if (col_off[c] >= 0)
+            tma_load_1d(dst + col_off[c], (const unsigned char*)p.ps.cols[c].ptr + row0 * p.col_w[c], (unsigned)(tile_rows * p.col_w[c]),
+                        &full[s]);
+      }
+    } else {
+      // ragged last tile: sizes need not be 16-byte multiples, so the warp copies it by hand
+      for (int c = 0; c < p.ps.ncols; c++) {
+        if (col_off[c] < 0) continue;
+        const unsigned char* src = (const unsigned char*)p.ps.cols[c].ptr + row0 * p.col_w[c];
+        const long long nb = left * p.col_w[c];
+        for (long long b = lane; b < nb; b += 32) dst[col_off[c] + b] = src[b];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    if (++s == S) { s = 0; ph ^= 1u; }
+  }
+}
 
 template <int DEPTH, int K, bool F64ONLY>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TILE = TM_CWARPS * 32 * K;
   TmaShared& sh = *reinterpret_cast<TmaShared*>(smem_raw);
-  unsigned char* stages = smem_raw + 1024;  // stage ring starts 1 KiB in (keeps 128-B alignment)
-  const int S = p.nstages;
+  unsigned char* ringA = smem_raw + TM_HDR_BYTES;
+  unsigned char* ringB = ringA + (size_t)p.nstagesA * p.stage_bytesA;
+  const int SA = p.nstagesA, SB = p.nstagesB;
+  const int LAG = p.lag;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
-    for (int s = 0; s < S; s++) {
-      mbar_init(&sh.full[s], 1);
-      mbar_init(&sh.empty[s], TM_CWARPS);
+    for (int s = 0; s < TM_MAX_STAGES; s++) {
+      mbar_init(&sh.fullA[s], 1);
+      mbar_init(&sh.emptyA[s], TM_CWARPS);
+      mbar_init(&sh.fullB[s], 1);
+      mbar_init(&sh.emptyB[s], TM_CWARPS);
     }
     for (int i = 0; i < TM_RING; i++) {
       mbar_init(&sh.cnt_ready[i], TM_CWARPS);
       mbar_init(&sh.pfx_ready[i], 1);
+      mbar_init(&sh.base_ready[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    sh.s_base[0] = 0;  // wave 0 starts from offset 0: its hand-off is pre-completed here
+    mbar_arrive(&sh.base_ready[0]);
   }
   __syncthreads();
 
   const int first = blockIdx.x, step = gridDim.x;
 
   if (warp == TM_CWARPS) {
-    // ================================ producer warp =============================================
-    int it = 0;
-    for (int tile = first; tile < p.ntiles; tile += step, ++it) {
-      const int s = it % S;
-      mbar_wait(&sh.empty[s], ((it / S) & 1) ^ 1);  // first pass over the ring returns immediately
-      unsigned char* dst = stages + (size_t)s * p.stage_bytes;
-      const long long row0 = (long long)tile * TILE;
-      const long long left = p.nrows - row0;
-      if (left >= TILE) {
-        if (lane == 0) {
-          unsigned total = 0;
-          for (int c = 0; c < p.ps.ncols; c++) total += (unsigned)(TILE * p.col_w[c]);
-          mbar_arrive_expect_tx(&sh.full[s], total);
-          for (int c = 0; c < p.ps.ncols; c++)
-            tma_load_1d(dst + p.col_off[c], (const unsigned char*)p.ps.cols[c].ptr + row0 * p.col_w[c], (unsigned)(TILE * p.col_w[c]),
-                        &sh.full[s]);
-        }
-      } else {
-        // ragged last tile: sizes need not be 16-byte multiples, so the warp copies it by hand
-        for (int c = 0; c < p.ps.ncols; c++) {
-          const unsigned char* src = (const unsigned char*)p.ps.cols[c].ptr + row0 * p.col_w[c];
-          const long long nb = left * p.col_w[c];
-          for (long long b = lane; b < nb; b += 32) dst[p.col_off[c] + b] = src[b];
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh.full[s]);
-      }
-    }
+    // ================================ producer A: predicate columns ============================
+    if (p.has_pred) producer_loop(p, TILE, p.col_offA, ringA, SA, p.stage_bytesA, sh.fullA, sh.emptyA, lane);
   } else if (warp == TM_CWARPS + 1) {
-    // ================================ scan warp =================================================
-    unsigned long long base = 0;  // selected rows in all earlier waves (identical in every CTA)
-    int it = 0;
-    for (int tile = first; tile < p.ntiles; tile += step, ++it) {
-      const int b = it % TM_RING;
-      mbar_wait(&sh.cnt_ready[b], (it / TM_RING) & 1);
-      const unsigned c = lane < TM_CWARPS ? sh.s_cnt[b][lane] : 0u;
-      unsigned incl = c;
+    // ================================ producer B: projection columns ===========================
+    // Runs as far ahead as ring B allows; the consumers reach these tiles LAG iterations after the
+    // predicate pass touched the same rows, so the bytes are L2 hits.
+    producer_loop(p, TILE, p.col_offB, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
+  } else if (warp >= TM_CWARPS + 2) {
+    // ================================ scan warps ================================================
+    if (!p.has_pred) return;  // nothing is dropped: output positions are the row numbers
+    const int sw = warp - (TM_CWARPS + 2);
+    int nloc = 0;
+    for (int tile = first; tile < p.ntiles; tile += step) nloc++;
+    // Each scan warp owns batches of TM_BATCH consecutive waves (batch j -> warp j % TM_SWARPS), so
+    // TM_SWARPS * TM_BATCH gathers are in flight per CTA: one gather is a full L2 round trip under
+    // load, several times longer than a tile.
+    for (int w0 = sw * TM_BATCH; w0 < nloc; w0 += TM_SWARPS * TM_BATCH) {
+      const int nb = min(TM_BATCH, nloc - w0);
+      unsigned excl[TM_BATCH];
+      unsigned long long total[TM_BATCH];
+      // 1. per-tile counts -> exclusive per-warp offsets, publish the tile totals
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+      for (int i = 0; i < TM_BATCH; i++) {
+        excl[i] = 0;
+        total[i] = 0;
+        if (i < nb) {
+          const int it = w0 + i, b = it % TM_RING;
+          mbar_wait(&sh.cnt_ready[b], (it / TM_RING) & 1);
+          const unsigned c = lane < TM_CWARPS ? sh.s_cnt[b][lane] : 0u;
+          unsigned incl = c;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          excl[i] = incl - c;
+          total[i] = __shfl_sync(0xffffffffu, incl, 31);
+          if (lane == 0) st_relaxed(&p.tile_status[first + it * step], ST_AGG | total[i]);
+        }
       }
-      const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
-      unsigned long long prefix;
-      if (!p.has_pred) {
-        prefix = (unsigned long long)tile * TILE;  // nothing is dropped: positions are known
-      } else {
-        if (lane == 0) st_relaxed(&p.tile_status[tile], ST_AGG | total);
-        // gather the counts of every tile of this wave: all loads issued before the first is used
-        const long long wave0 = (long long)it * step;
-        unsigned long long sv[TM_MAX_GRID / 32];
+      // 2. gather the counts of every tile of these waves: all loads issued before any is used
+      unsigned long long sv[TM_BATCH][TM_MAX_GRID / 32];
+#pragma unroll
+      for (int i = 0; i < TM_BATCH; i++) {
+        const long long wave0 = (long long)(w0 + i) * step;
 #pragma unroll
         for (int w = 0; w < TM_MAX_GRID / 32; w++) {
           const int j = w * 32 + lane;
           const long long idx = wave0 + j;
-          sv[w] = (w * 32 < step && j < step && idx < p.ntiles) ? ld_relaxed(&p.tile_status[idx]) : ST_AGG;
+          sv[i][w] = (i < nb && w * 32 < step && j < step && idx < p.ntiles) ? ld_relaxed(&p.tile_status[idx]) : ST_AGG;
         }
-        unsigned long long before = 0, wave_total = 0;
+      }
+      unsigned long long before[TM_BATCH], wave_total[TM_BATCH];
+#pragma unroll
+      for (int i = 0; i < TM_BATCH; i++) {
+        const long long wave0 = (long long)(w0 + i) * step;
+        unsigned long long bf = 0, wt = 0;
 #pragma unroll
         for (int w = 0; w < TM_MAX_GRID / 32; w++) {
-          if (w * 32 < step) {
+          if (i < nb && w * 32 < step) {
             const int j = w * 32 + lane;
             const long long idx = wave0 + j;
-            while (__any_sync(0xffffffffu, (sv[w] >> 62) == 0)) {
-              if ((sv[w] >> 62) == 0) sv[w] = ld_relaxed(&p.tile_status[idx]);
+            while (__any_sync(0xffffffffu, (sv[i][w] >> 62) == 0)) {
+              if ((sv[i][w] >> 62) == 0) sv[i][w] = ld_relaxed(&p.tile_status[idx]);
             }
-            const unsigned long long v = sv[w] & ST_MASK;
-            wave_total += v;
-            if (j < (int)blockIdx.x) before += v;
+            const unsigned long long v = sv[i][w] & ST_MASK;
+            wt += v;
+            if (j < (int)blockIdx.x) bf += v;
           }
         }
-        before = warp_sum64(before);
-        wave_total = warp_sum64(wave_total);
-        prefix = base + before;
-        base += wave_total;
+        before[i] = warp_sum64(bf);
+        wave_total[i] = warp_sum64(wt);
       }
-      if (lane < TM_CWARPS) sh.s_off[b][lane] = prefix + (incl - c);
-      if (lane == 0 && tile == p.ntiles - 1) *p.out_count = prefix + total;
+      // 3. running base: handed from the scan warp of the previous batch through shared memory
+      const int hb = (w0 / TM_BATCH) % TM_RING;
+      mbar_wait(&sh.base_ready[hb], ((w0 / TM_BATCH) / TM_RING) & 1);
+      unsigned long long base = sh.s_base[hb];
+#pragma unroll
+      for (int i = 0; i < TM_BATCH; i++) {
+        if (i < nb) {
+          const int it = w0 + i, b = it % TM_RING;
+          if (lane < TM_CWARPS) sh.s_off[b][lane] = base + before[i] + excl[i];
+          if (lane == 0 && first + it * step == p.ntiles - 1) *p.out_count = base + before[i] + total[i];
+          base += wave_total[i];
+        }
+      }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.pfx_ready[b]);
+      if (lane == 0) {
+        const int nh = (w0 / TM_BATCH + 1) % TM_RING;
+        sh.s_base[nh] = base;
+        mbar_arrive(&sh.base_ready[nh]);
+        for (int i = 0; i < nb; i++) mbar_arrive(&sh.pfx_ready[(w0 + i) % TM_RING]);
+      }
     }
   } else {
     // ================================ consumer warps ============================================
     const unsigned lt_mask = (1u << lane) - 1u;
+    constexpr unsigned KMASK = (1u << K) - 1u;
     bool bad = false;
 
-    // predicate of local iteration `it` -> flag bits (bit k = row warp*32*K + k*32 + lane of the tile)
-    auto phase1 = [&](int it, int tile) -> unsigned {
-      const int s = it % S;
-      mbar_wait(&sh.full[s], (it / S) & 1);
+    // predicate of local iteration `it` -> K flag bits (bit k = row warp*32*K + k*32 + lane of the tile)
+    auto phase1 = [&](int it, int tile, int s, unsigned ph) -> unsigned {
+      mbar_wait(&sh.fullA[s], ph);
       StagedTile<K> src;
-      src.stage = stages + (size_t)s * p.stage_bytes;
-      src.col_off = p.col_off;
+      src.stage = ringA + (size_t)s * p.stage_bytesA;
+      src.col_off = p.col_offA;
       src.lrow0 = warp * 32 * K + lane;
-      const long long row0 = (long long)tile * TILE + src.lrow0;
-      src.valid = 0;
+      src.valid = KMASK;
+      if (tile == p.ntiles - 1) {  // only the last tile can be ragged
+        const long long row0 = (long long)tile * TILE + src.lrow0;
+        src.valid = 0;
 #pragma unroll
-      for (int k = 0; k < K; k++)
-        if (row0 + k * 32 < p.nrows) src.valid |= 1u << k;
-      unsigned flags = src.valid;
-      if (p.has_pred && p.pred_fast.kind >= 2) {
+        for (int k = 0; k < K; k++)
+          if (row0 + k * 32 < p.nrows) src.valid |= 1u << k;
+      }
+      unsigned flags;
+      if (p.pred_fast.kind >= 2) {
         // fast shape: one Float64 comparison, operands straight from the staged tile
-        const double* A = (const double*)(src.stage + p.col_off[p.pred_fast.a]) + src.lrow0;
+        const double* A = (const double*)(src.stage + p.col_offA[p.pred_fast.a]) + src.lrow0;
         const bool bcol = p.pred_fast.kind == 2;
-        const double* B = bcol ? (const double*)(src.stage + p.col_off[p.pred_fast.b]) + src.lrow0 : A;
+        const double* B = bcol ? (const double*)(src.stage + p.col_offA[p.pred_fast.b]) + src.lrow0 : A;
         const double imm = p.pred_fast.imm;
         flags = 0;
-#define DF_CMP(OPR)                                                        \
-  if (bcol) {                                                              \
-    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR B[k * 32]) << k; \
-  } else {                                                                 \
-    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR imm) << k;       \
+#define DF_CMP(OPR)                                                                                    \
+  if (bcol) {                                                                                          \
+    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR B[k * 32]) << k;   \
+  } else {                                                                                             \
+    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR imm) << k;         \
   }
         switch (p.pred_fast.op) {
           case V_EQ: DF_CMP(==) break;
@@ -224,20 +294,21 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           default: DF_CMP(>=) break;
         }
 #undef DF_CMP
-        flags &= src.valid;
-      } else if (p.has_pred) {
+      } else {
         unsigned long long v[K];
         const unsigned b = eval_program<DEPTH, K, F64ONLY>(p.ps, 0, src, v);
         bad = bad || (b != 0);
         flags = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) flags |= (unsigned)(v[k] & 1ull) << k;
-        flags &= src.valid;
       }
+      flags &= src.valid;
       unsigned cnt = 0;
 #pragma unroll
       for (int k = 0; k < K; k++) cnt += __popc(__ballot_sync(0xffffffffu, (flags >> k) & 1u));
+      __syncwarp();
       if (lane == 0) {
+        mbar_arrive(&sh.emptyA[s]);  // this warp is done reading the stage
         sh.s_cnt[it % TM_RING][warp] = cnt;
         mbar_arrive(&sh.cnt_ready[it % TM_RING]);
       }
@@ -245,13 +316,18 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
     };
 
     // projections of local iteration `it`: selected rows go to their compacted global position
-    auto phase2 = [&](int it, int tile, unsigned flags) {
-      const int s = it % S;
-      mbar_wait(&sh.pfx_ready[it % TM_RING], (it / TM_RING) & 1);
-      const unsigned long long base = sh.s_off[it % TM_RING][warp];
+    auto phase2 = [&](int it, int tile, unsigned flags, int s, unsigned ph) {
+      unsigned long long base;
+      if (p.has_pred) {
+        mbar_wait(&sh.pfx_ready[it % TM_RING], (it / TM_RING) & 1);
+        base = sh.s_off[it % TM_RING][warp];
+      } else {
+        base = (unsigned long long)tile * TILE + (unsigned long long)warp * 32 * K;
+      }
+      mbar_wait(&sh.fullB[s], ph);
       StagedTile<K> src;
-      src.stage = stages + (size_t)s * p.stage_bytes;
-      src.col_off = p.col_off;
+      src.stage = ringB + (size_t)s * p.stage_bytesB;
+      src.col_off = p.col_offB;
       src.lrow0 = warp * 32 * K + lane;
       src.valid = flags;  // a zero divisor only matters on rows that survive the filter
       for (int q = 0; q < p.nproj; q++) {
@@ -259,13 +335,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         unsigned long long v[K];
         const FastOp& fo = p.proj_fast[q];
         if (fo.kind == 1) {
-          const unsigned long long* A = (const unsigned long long*)(src.stage + p.col_off[fo.a]) + src.lrow0;
+          const unsigned long long* A = (const unsigned long long*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
 #pragma unroll
           for (int k = 0; k < K; k++) v[k] = A[k * 32];
         } else if (fo.kind >= 2) {
-          const double* A = (const double*)(src.stage + p.col_off[fo.a]) + src.lrow0;
+          const double* A = (const double*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
           const bool bcol = fo.kind == 2;
-          const double* B = bcol ? (const double*)(src.stage + p.col_off[fo.b]) + src.lrow0 : A;
+          const double* B = bcol ? (const double*)(src.stage + p.col_offB[fo.b]) + src.lrow0 : A;
           const double imm = fo.imm;
           double y[K];
 #pragma unroll
@@ -296,38 +372,64 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           bad = bad || (b != 0);
         }
         const int odt = p.ps.out_dtype[prog];
-        void* o = p.out[q];
-        unsigned long long run = base;
+        const bool wide = F64ONLY || fo.kind;
+        // warp-local base pointer once (64-bit), then 32-bit running offsets
+        unsigned char* o = (unsigned char*)p.out[q] + base * (unsigned long long)(wide ? 8 : dtype_width_dev(odt));
+        unsigned run = 0;
 #pragma unroll
         for (int k = 0; k < K; k++) {
           const bool f = (flags >> k) & 1u;
           const unsigned m = __ballot_sync(0xffffffffu, f);
           if (f) {
-            const long long idx = (long long)(run + __popc(m & lt_mask));
-            if (F64ONLY || fo.kind) ((unsigned long long*)o)[idx] = v[k];
-            else store_elem(o, odt, idx, v[k]);
+            const unsigned idx = run + __popc(m & lt_mask);
+            if (wide) ((unsigned long long*)o)[idx] = v[k];
+            else store_elem(o, odt, (long long)idx, v[k]);
           }
           run += __popc(m);
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.empty[s]);  // this warp is done reading the stage
+      if (lane == 0) mbar_arrive(&sh.emptyB[s]);
     };
 
-    // software pipeline: predicate of tile it, then projections of tile it - TM_LAG
-    static_assert(TM_LAG == 2, "the flag registers below are written out for a lag of 2");
-    int it = 0;
-    unsigned f1 = 0, f2 = 0;  // flags of tiles it-1, it-2
-    int t1 = -1, t2 = -1;
-    for (int tile = first; tile < p.ntiles; tile += step, ++it) {
-      const unsigned f0 = phase1(it, tile);
-      if (it >= TM_LAG) phase2(it - TM_LAG, t2, f2);
-      f2 = f1; t2 = t1;
-      f1 = f0; t1 = tile;
+    int nloc = 0;
+    for (int tile = first; tile < p.ntiles; tile += step) nloc++;
+    int sb = 0;
+    unsigned phb = 0;
+    if (!p.has_pred) {
+      // pure projection: no predicate pass, no lag
+      for (int it = 0; it < nloc; it++) {
+        const int tile = first + it * step;
+        unsigned valid = KMASK;
+        if (tile == p.ntiles - 1) {
+          const long long row0 = (long long)tile * TILE + warp * 32 * K + lane;
+          valid = 0;
+#pragma unroll
+          for (int k = 0; k < K; k++)
+            if (row0 + k * 32 < p.nrows) valid |= 1u << k;
+        }
+        phase2(it, tile, valid, sb, phb);
+        if (++sb == SB) { sb = 0; phb ^= 1u; }
+      }
+    } else {
+      // software pipeline: predicate of tile it, projections of tile it - LAG; the flag bits of the
+      // last LAG+1 tiles live in a 64-bit shift register (K bits per tile)
+      unsigned long long fl = 0;
+      int sa = 0;
+      unsigned pha = 0;
+      for (int it = 0; it < nloc + LAG; it++) {
+        unsigned f0 = 0;
+        if (it < nloc) {
+          f0 = phase1(it, first + it * step, sa, pha);
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+        fl = (fl << K) | (unsigned long long)f0;
+        if (it >= LAG) {
+          phase2(it - LAG, first + (it - LAG) * step, (unsigned)(fl >> (K * LAG)) & KMASK, sb, phb);
+          if (++sb == SB) { sb = 0; phb ^= 1u; }
+        }
+      }
     }
-    // drain
-    if (it >= 2) phase2(it - 2, t2, f2);
-    if (it >= 1) phase2(it - 1, t1, f1);
     if (bad) *p.err_flag = 1u;
   }
 }
@@ -337,7 +439,7 @@ static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   auto kern = k_filter_project_tma<DEPTH, K, F64ONLY>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 2048));
+    DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + TM_HDR_BYTES));
     configured = true;
   }
   long long grid = std::min(ctx->sm_count, TM_MAX_GRID);  // one persistent CTA per SM
@@ -358,31 +460,54 @@ static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
 
 bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   if (p.ps.max_depth > 4 || p.ps.ncols < 1) return false;
-  int row_bytes = 0;
+  // which column slots does the predicate read, which do the projections read?
+  bool inA[kMaxCols] = {}, inB[kMaxCols] = {};
+  for (int prog = 0; prog < p.ps.nprog; prog++) {
+    bool* dst = (p.has_pred && prog == 0) ? inA : inB;
+    for (int pc = p.ps.start[prog]; pc < p.ps.start[prog + 1]; pc++) {
+      const DevInsn& di = p.ps.insn[pc];
+      if (di.op == V_PUSH_COL || (di.op > V_CAST && di.mode == RHS_COL)) dst[di.slot] = true;
+    }
+  }
+  int rowA = 0, rowB = 0;
   for (int c = 0; c < p.ps.ncols; c++) {
     p.col_w[c] = dtype_width(p.ps.cols[c].dtype);
     if (p.col_w[c] <= 0) return false;
-    row_bytes += p.col_w[c];
+    if (inA[c]) rowA += p.col_w[c];
+    if (inB[c]) rowB += p.col_w[c];
   }
-  // rows per lane K in {8,4,2}: the biggest tile that still leaves TM_LAG + 3 stages in shared
-  // memory (TM_LAG + 1 tiles are held by the consumers, the rest is prefetch depth)
+  // projections of literals only, or a predicate over literals only: leave to the direct kernel
+  if (rowB == 0 || (p.has_pred && rowA == 0)) return false;
+  // rows per lane K in {8,4,2}: the biggest tile that still gives both rings >= 5 stages (>= 3 as a
+  // last resort): enough bulk copies in flight per SM to cover the HBM latency
   int K = 0;
-  for (int k : {8, 4, 2}) {
-    if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
-    const long long tile = (long long)TM_CWARPS * 32 * k;
-    if (tile * row_bytes * (TM_LAG + 3) <= TM_SMEM_BUDGET) { K = k; break; }
+  for (int want : {5, 3}) {
+    for (int k : {8, 4, 2}) {
+      if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
+      const long long tile = (long long)TM_CWARPS * 32 * k;
+      if (tile * (rowA + rowB) * want <= TM_SMEM_BUDGET) { K = k; break; }
+    }
+    if (K) break;
   }
   if (!K) return false;
   const int tile = TM_CWARPS * 32 * K;
-  int off = 0;
+  int offA = 0, offB = 0;
   for (int c = 0; c < p.ps.ncols; c++) {
-    p.col_off[c] = off;
-    off += tile * p.col_w[c];  // tile is a multiple of 512 rows: every column slice stays 128-B aligned
+    // tile is a multiple of 512 rows: every column slice stays 128-B aligned
+    p.col_offA[c] = inA[c] ? offA : -1;
+    if (inA[c]) offA += tile * p.col_w[c];
+    p.col_offB[c] = inB[c] ? offB : -1;
+    if (inB[c]) offB += tile * p.col_w[c];
   }
-  p.stage_bytes = off;
-  p.nstages = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / p.stage_bytes);
+  p.stage_bytesA = offA;
+  p.stage_bytesB = offB;
+  const int S = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / (offA + offB));
+  p.nstagesA = offA ? S : 0;
+  p.nstagesB = S;
+  if (!p.has_pred) p.nstagesB = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / offB);
+  p.lag = p.has_pred ? std::min(TM_MAX_LAG, 64 / K - 1) : 0;
   p.ntiles = int((p.nrows + tile - 1) / tile);
-  const size_t smem = 1024 + (size_t)p.nstages * p.stage_bytes;
+  const size_t smem = TM_HDR_BYTES + (size_t)p.nstagesA * p.stage_bytesA + (size_t)p.nstagesB * p.stage_bytesB;
   const int d = p.ps.max_depth;
   if (K == 8) launch_k<2, 8>(ctx, p, smem);
   else if (K == 4) { if (d <= 2) launch_k<2, 4>(ctx, p, smem); else launch_k<4, 4>(ctx, p, smem); }
