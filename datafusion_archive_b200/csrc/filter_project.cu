@@ -272,7 +272,40 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       return f;
     };
     memset(&p.pred_fast, 0, sizeof(p.pred_fast));
-    if (has_pred) p.pred_fast = fast_of(0, true);
+    if (has_pred) {
+      // t0 [t1 AND|OR [t2 AND|OR ...]] in lowered form: (PUSH_COL, CMP leaf) {(PUSH_COL, CMP leaf), AND|OR stack}*
+      const int b = p.ps.start[0], e = p.ps.start[1];
+      const DevInsn* in = &p.ps.insn[b];
+      auto term_at = [&](int i, FastOp* out) {
+        if (i + 1 >= e - b) return false;
+        const DevInsn &c = in[i], &o = in[i + 1];
+        if (c.op != V_PUSH_COL || p.ps.cols[c.slot].dtype != DFGPU_FLOAT64) return false;
+        if (o.op < V_EQ || o.op > V_GE || o.mtype != MT_F64 || o.mode == RHS_STACK) return false;
+        if (o.mode == RHS_COL && p.ps.cols[o.slot].dtype != DFGPU_FLOAT64) return false;
+        memset(out, 0, sizeof(*out));
+        out->kind = o.mode == RHS_COL ? 2 : 3;
+        out->op = o.op;
+        out->a = c.slot;
+        out->b = o.slot;
+        memcpy(&out->imm, &o.imm, 8);
+        return true;
+      };
+      FastPred fp;
+      memset(&fp, 0, sizeof(fp));
+      int i = 0;
+      bool ok = term_at(0, &fp.term[0]);
+      fp.nterms = ok ? 1 : 0;
+      i = 2;
+      while (ok && i < e - b) {
+        if (fp.nterms >= 4 || !term_at(i, &fp.term[fp.nterms]) || i + 2 >= e - b) { ok = false; break; }
+        const DevInsn& j = in[i + 2];
+        if ((j.op != V_AND && j.op != V_OR) || j.mode != RHS_STACK) { ok = false; break; }
+        fp.conn[fp.nterms] = j.op == V_OR ? 1 : 0;
+        fp.nterms++;
+        i += 3;
+      }
+      if (ok) p.pred_fast = fp;
+    }
     for (int i = 0; i < nproj; i++) p.proj_fast[i] = fast_of(i + has_pred, false);
     if (ctx->force_direct_kernel || !launch_fp_tma(ctx, p)) {
       p.ntiles = int((n + FP_TILE - 1) / FP_TILE);

@@ -19,6 +19,14 @@ struct FastOp {
   double imm;
 };
 
+// predicate fast shape: up to 4 Float64 comparisons chained left to right with AND / OR
+//   t0 [conn1 t1 [conn2 t2 [conn3 t3]]]   (each term: COL cmp COL | COL cmp IMM)
+struct FastPred {
+  int nterms;  // 0 = use the interpreter
+  int conn[4]; // conn[i] joins the running result with term i: 0 = AND, 1 = OR
+  FastOp term[4];
+};
+
 struct FPParams {
   ProgramSet ps;  // program 0 = predicate when has_pred, projections follow
   void* out[kMaxProgs];
@@ -40,9 +48,9 @@ struct FPParams {
   int lag;  // tiles between the predicate pass and the projection pass
   // "fast shapes": single-operation Float64 programs are recognised on the host and executed by
   // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).
-  //   predicate : COL cmp COL | COL cmp IMM
+  //   predicate : chain of (COL cmp COL | COL cmp IMM) joined by AND / OR
   //   projection: COL | COL op COL | COL op IMM          (op in + - * /)
-  FastOp pred_fast;
+  FastPred pred_fast;
   FastOp proj_fast[kMaxProgs];
 };
 

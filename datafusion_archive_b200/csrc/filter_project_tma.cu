@@ -124,6 +124,32 @@ __device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, 
   }
 }
 
+// one Float64 comparison over the K rows of this lane -> K flag bits
+template <int K>
+__device__ __forceinline__ unsigned cmp_term(const FastOp& t, const unsigned char* stage, const int* col_off, int lrow0) {
+  const double* A = (const double*)(stage + col_off[t.a]) + lrow0;
+  const bool bcol = t.kind == 2;
+  const double* B = bcol ? (const double*)(stage + col_off[t.b]) + lrow0 : A;
+  const double imm = t.imm;
+  unsigned flags = 0;
+#define DF_CMP(OPR)                                                                                    \
+  if (bcol) {                                                                                          \
+    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR B[k * 32]) << k;   \
+  } else {                                                                                             \
+    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR imm) << k;         \
+  }
+  switch (t.op) {
+    case V_EQ: DF_CMP(==) break;
+    case V_NE: DF_CMP(!=) break;
+    case V_LT: DF_CMP(<) break;
+    case V_LE: DF_CMP(<=) break;
+    case V_GT: DF_CMP(>) break;
+    default: DF_CMP(>=) break;
+  }
+#undef DF_CMP
+  return flags;
+}
+
 template <int DEPTH, int K, bool F64ONLY>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -272,28 +298,13 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           if (row0 + k * 32 < p.nrows) src.valid |= 1u << k;
       }
       unsigned flags;
-      if (p.pred_fast.kind >= 2) {
-        // fast shape: one Float64 comparison, operands straight from the staged tile
-        const double* A = (const double*)(src.stage + p.col_offA[p.pred_fast.a]) + src.lrow0;
-        const bool bcol = p.pred_fast.kind == 2;
-        const double* B = bcol ? (const double*)(src.stage + p.col_offA[p.pred_fast.b]) + src.lrow0 : A;
-        const double imm = p.pred_fast.imm;
-        flags = 0;
-#define DF_CMP(OPR)                                                                                    \
-  if (bcol) {                                                                                          \
-    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR B[k * 32]) << k;   \
-  } else {                                                                                             \
-    _Pragma("unroll") for (int k = 0; k < K; k++) flags |= (unsigned)(A[k * 32] OPR imm) << k;         \
-  }
-        switch (p.pred_fast.op) {
-          case V_EQ: DF_CMP(==) break;
-          case V_NE: DF_CMP(!=) break;
-          case V_LT: DF_CMP(<) break;
-          case V_LE: DF_CMP(<=) break;
-          case V_GT: DF_CMP(>) break;
-          default: DF_CMP(>=) break;
+      if (p.pred_fast.nterms > 0) {
+        // fast shape: Float64 comparisons straight from the staged tile, joined by AND / OR
+        flags = cmp_term<K>(p.pred_fast.term[0], src.stage, p.col_offA, src.lrow0);
+        for (int t = 1; t < p.pred_fast.nterms; t++) {
+          const unsigned ft = cmp_term<K>(p.pred_fast.term[t], src.stage, p.col_offA, src.lrow0);
+          flags = p.pred_fast.conn[t] ? (flags | ft) : (flags & ft);
         }
-#undef DF_CMP
       } else {
         unsigned long long v[K];
         const unsigned b = eval_program<DEPTH, K, F64ONLY>(p.ps, 0, src, v);
@@ -478,16 +489,18 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   }
   // projections of literals only, or a predicate over literals only: leave to the direct kernel
   if (rowB == 0 || (p.has_pred && rowA == 0)) return false;
-  // rows per lane K in {8,4,2}: the biggest tile that still gives both rings >= 5 stages (>= 3 as a
-  // last resort): enough bulk copies in flight per SM to cover the HBM latency
+  // rows per lane K in {8,4,2}: the biggest tile that still gives both rings 3 stages.  Measured on
+  // B200 (profiles/r01_microbench_fp.txt): per-tile fixed costs (barrier hand-offs, offset gather)
+  // outweigh deeper prefetch, so bigger tiles with 3 stages beat smaller tiles with 6.
   int K = 0;
-  for (int want : {5, 3}) {
-    for (int k : {8, 4, 2}) {
-      if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
-      const long long tile = (long long)TM_CWARPS * 32 * k;
-      if (tile * (rowA + rowB) * want <= TM_SMEM_BUDGET) { K = k; break; }
-    }
-    if (K) break;
+  for (int k : {8, 4, 2}) {
+    if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
+    const long long tile = (long long)TM_CWARPS * 32 * k;
+    if (tile * (rowA + rowB) * 3 <= TM_SMEM_BUDGET) { K = k; break; }
+  }
+  if (const char* e = getenv("DFGPU_FP_K")) {  // experiment knob
+    const int k = atoi(e);
+    if ((k == 8 || k == 4 || k == 2) && (long long)TM_CWARPS * 32 * k * (rowA + rowB) * 2 <= TM_SMEM_BUDGET && !(k == 8 && p.ps.max_depth > 2)) K = k;
   }
   if (!K) return false;
   const int tile = TM_CWARPS * 32 * K;
