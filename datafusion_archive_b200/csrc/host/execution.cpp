@@ -1,0 +1,494 @@
+// execution.cpp — see execution.h.
+#include "execution.h"
+
+#include <cstring>
+#include <set>
+
+namespace dfhost {
+
+namespace {
+[[noreturn]] void gpu_fail(int rc) { fail(rc, dfgpu_last_error()); }
+#define GPU_CHECK(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) gpu_fail(_rc); \
+  } while (0)
+}  // namespace
+
+dfgpu_col Array::view() const {
+  dfgpu_col c;
+  memset(&c, 0, sizeof(c));
+  c.dtype = data_type;
+  c.len = len;
+  c.offset = offset;
+  c.values = values;
+  c.validity = null_count > 0 ? validity : nullptr;
+  c.offsets = offsets;
+  c.values_bytes = values_bytes;
+  return c;
+}
+
+// ---- CSV -----------------------------------------------------------------------------------------
+CsvDataSource::CsvDataSource(const std::string& filename, SchemaRef schema, size_t batch_size)
+    : schema_(std::move(schema)), file_(filename), batch_size_(batch_size ? batch_size : 1024) {
+  if (!file_.is_open()) fail(DFGPU_ERR_GENERAL, "IoError: cannot open " + filename);
+}
+
+static std::vector<std::string> split_csv_line(const std::string& line) {
+  std::vector<std::string> out;
+  std::string cur;
+  bool inq = false;
+  for (size_t i = 0; i < line.size(); i++) {
+    char c = line[i];
+    if (inq) {
+      if (c == '"') {
+        if (i + 1 < line.size() && line[i + 1] == '"') { cur += '"'; i++; }
+        else inq = false;
+      } else cur += c;
+    } else if (c == '"') inq = true;
+    else if (c == ',') { out.push_back(cur); cur.clear(); }
+    else if (c == '\r') {}
+    else cur += c;
+  }
+  out.push_back(cur);
+  return out;
+}
+
+template <class T>
+static void push_val(Array& a, T v) {
+  size_t n = a.own_values.size();
+  a.own_values.resize(n + sizeof(T));
+  memcpy(a.own_values.data() + n, &v, sizeof(T));
+}
+
+std::optional<RecordBatch> CsvDataSource::next() {
+  std::string line;
+  if (!header_skipped_) {
+    header_skipped_ = true;
+    std::getline(file_, line);  // has_headers = true, unconditionally (datasource.rs:41)
+    line_no_++;
+  }
+  RecordBatch b;
+  b.schema = schema_;
+  for (auto& f : schema_->fields) {
+    auto a = std::make_shared<Array>();
+    a->data_type = f.data_type;
+    if (f.data_type == DFGPU_UTF8) a->own_offsets.push_back(0);
+    b.columns.push_back(a);
+  }
+  size_t rows = 0;
+  while (rows < batch_size_ && std::getline(file_, line)) {
+    line_no_++;
+    if (line.empty()) continue;
+    auto fields = split_csv_line(line);
+    if (fields.size() < schema_->fields.size())
+      fail(DFGPU_ERR_ARROW, "ParseError(\"line " + std::to_string(line_no_) + " has too few columns\")");
+    for (size_t c = 0; c < schema_->fields.size(); c++) {
+      Array& a = *b.columns[c];
+      const std::string& s = fields[c];
+      char* end = nullptr;
+      switch (a.data_type) {
+        case DFGPU_UTF8:
+          a.own_values.insert(a.own_values.end(), s.begin(), s.end());
+          a.own_offsets.push_back(int32_t(a.own_values.size()));
+          break;
+        case DFGPU_FLOAT64: { double v = strtod(s.c_str(), &end); if (end == s.c_str()) goto bad; push_val(a, v); break; }
+        case DFGPU_FLOAT32: { float v = strtof(s.c_str(), &end); if (end == s.c_str()) goto bad; push_val(a, v); break; }
+        case DFGPU_INT8: { long long v = strtoll(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, int8_t(v)); break; }
+        case DFGPU_INT16: { long long v = strtoll(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, int16_t(v)); break; }
+        case DFGPU_INT32: { long long v = strtoll(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, int32_t(v)); break; }
+        case DFGPU_INT64: { long long v = strtoll(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, int64_t(v)); break; }
+        case DFGPU_UINT8: { unsigned long long v = strtoull(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, uint8_t(v)); break; }
+        case DFGPU_UINT16: { unsigned long long v = strtoull(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, uint16_t(v)); break; }
+        case DFGPU_UINT32: { unsigned long long v = strtoull(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, uint32_t(v)); break; }
+        case DFGPU_UINT64: { unsigned long long v = strtoull(s.c_str(), &end, 10); if (end == s.c_str()) goto bad; push_val(a, uint64_t(v)); break; }
+        default: fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("CSV column type ") + datatype_debug(a.data_type));
+      }
+      continue;
+    bad:
+      fail(DFGPU_ERR_ARROW, "ParseError(\"Error while parsing value " + s + " at line " + std::to_string(line_no_) + "\")");
+    }
+    rows++;
+  }
+  if (rows == 0) return std::nullopt;
+  for (auto& a : b.columns) {
+    a->len = int64_t(rows);
+    a->values = a->own_values.data();
+    a->values_bytes = int64_t(a->own_values.size());
+    if (a->data_type == DFGPU_UTF8) a->offsets = a->own_offsets.data();
+  }
+  b.num_rows = int64_t(rows);
+  return b;
+}
+
+// ---- memory source ----------------------------------------------------------------------------------
+MemoryDataSource::MemoryDataSource(SchemaRef schema, std::vector<ArrayRef> cols, size_t batch_size)
+    : schema_(std::move(schema)), cols_(std::move(cols)) {
+  nrows_ = cols_.empty() ? 0 : cols_[0]->len;
+  for (auto& c : cols_)
+    if (c->len != nrows_) fail(DFGPU_ERR_GENERAL, "all columns of a table must have the same length");
+  batch_size_ = batch_size ? int64_t(batch_size) : (nrows_ > 0 ? nrows_ : 1);
+}
+
+std::optional<RecordBatch> MemoryDataSource::next() {
+  if (pos_ >= nrows_) return std::nullopt;
+  const int64_t n = std::min(batch_size_, nrows_ - pos_);
+  RecordBatch b;
+  b.schema = schema_;
+  b.num_rows = n;
+  for (auto& c : cols_) {
+    auto s = std::make_shared<Array>(*c);  // shares the borrowed pointers
+    s->offset = c->offset + pos_;
+    s->len = n;
+    b.columns.push_back(s);
+  }
+  pos_ += n;
+  return b;
+}
+
+// ---- Expr -> postfix program of the C ABI -------------------------------------------------------------
+namespace {
+
+void collect_columns(const Expr& e, std::set<size_t>& acc) {  // collect_expr, sqlplanner.rs:435-458
+  switch (e.kind) {
+    case Expr::Column: acc.insert(e.index); break;
+    case Expr::BinaryExpr: collect_columns(*e.left, acc); collect_columns(*e.right, acc); break;
+    case Expr::Cast: case Expr::IsNull: case Expr::IsNotNull: case Expr::Sort: collect_columns(*e.left, acc); break;
+    case Expr::ScalarFunction: case Expr::AggregateFunction:
+      for (auto& a : e.args) collect_columns(*a, acc);
+      break;
+    default: break;
+  }
+}
+
+void lower(const Expr& e, const Schema& schema, const std::map<size_t, int>& remap, std::vector<dfgpu_insn>& out) {
+  dfgpu_insn in;
+  memset(&in, 0, sizeof(in));
+  switch (e.kind) {
+    case Expr::Column: {
+      auto it = remap.find(e.index);
+      if (it == remap.end()) fail(DFGPU_ERR_INVALID_COLUMN, "column index out of range");
+      in.op = DFGPU_OP_COL;
+      in.col = it->second;
+      in.dtype = schema.fields[e.index].data_type;
+      out.push_back(in);
+      return;
+    }
+    case Expr::Literal: {
+      const ScalarValue& v = e.value;
+      if (!(v.dtype >= DFGPU_INT8 && v.dtype <= DFGPU_FLOAT64))
+        fail(DFGPU_ERR_EXECUTION, "No support for literal type " + v.debug());  // expression.rs:306-309
+      in.op = DFGPU_OP_LIT;
+      in.dtype = v.dtype;
+      if (v.dtype == DFGPU_FLOAT64) in.lit.f64 = v.v.d;
+      else if (v.dtype == DFGPU_FLOAT32) { in.lit.u64 = 0; in.lit.f32 = v.v.f; }
+      else in.lit.u64 = v.v.u;
+      out.push_back(in);
+      return;
+    }
+    case Expr::Cast:
+      lower(*e.left, schema, remap, out);
+      in.op = DFGPU_OP_CAST;
+      in.dtype = e.data_type;
+      in.col = e.left->kind == Expr::Literal ? e.left->value.dtype : (e.left->kind == Expr::Column ? schema.fields[e.left->index].data_type : 0);
+      out.push_back(in);
+      return;
+    case Expr::BinaryExpr: {
+      lower(*e.left, schema, remap, out);
+      lower(*e.right, schema, remap, out);
+      switch (e.op) {
+        case Operator::Eq: in.op = DFGPU_OP_EQ; break;
+        case Operator::NotEq: in.op = DFGPU_OP_NE; break;
+        case Operator::Lt: in.op = DFGPU_OP_LT; break;
+        case Operator::LtEq: in.op = DFGPU_OP_LE; break;
+        case Operator::Gt: in.op = DFGPU_OP_GT; break;
+        case Operator::GtEq: in.op = DFGPU_OP_GE; break;
+        case Operator::And: in.op = DFGPU_OP_AND; break;
+        case Operator::Or: in.op = DFGPU_OP_OR; break;
+        case Operator::Plus: in.op = DFGPU_OP_ADD; break;
+        case Operator::Minus: in.op = DFGPU_OP_SUB; break;
+        case Operator::Multiply: in.op = DFGPU_OP_MUL; break;
+        case Operator::Divide: in.op = DFGPU_OP_DIV; break;
+        default: fail(DFGPU_ERR_EXECUTION, std::string("operator: ") + operator_debug(e.op));  // expression.rs:494-497
+      }
+      out.push_back(in);
+      return;
+    }
+    default: fail(DFGPU_ERR_EXECUTION, "expression " + e.debug());  // expression.rs:500-503
+  }
+}
+
+// Rust `{}` (Display) of a number, as literal_array! names its closure (expression.rs:230)
+std::string display_number(const ScalarValue& v) {
+  switch (v.dtype) {
+    case DFGPU_FLOAT64: { std::string s = rust_debug_f64(v.v.d); if (s.size() > 2 && s.compare(s.size() - 2, 2, ".0") == 0) s.resize(s.size() - 2); return s; }
+    case DFGPU_FLOAT32: { std::string s = rust_debug_f64(double(v.v.f)); if (s.size() > 2 && s.compare(s.size() - 2, 2, ".0") == 0) s.resize(s.size() - 2); return s; }
+    case DFGPU_INT8: case DFGPU_INT16: case DFGPU_INT32: case DFGPU_INT64: return std::to_string(v.v.i);
+    default: return std::to_string(v.v.u);
+  }
+}
+
+struct Pruned {
+  std::map<size_t, int> remap;       // input column index -> uploaded column index
+  std::vector<size_t> cols;          // uploaded column -> input column index
+};
+
+Pruned prune(const std::vector<ExprRef>& exprs, size_t ncols, bool all) {
+  std::set<size_t> acc;
+  if (all) for (size_t i = 0; i < ncols; i++) acc.insert(i);
+  for (auto& e : exprs) if (e) collect_columns(*e, acc);
+  Pruned p;
+  for (size_t c : acc) {
+    if (c >= ncols) fail(DFGPU_ERR_INVALID_COLUMN, "column index out of range");
+    p.remap[c] = int(p.cols.size());
+    p.cols.push_back(c);
+  }
+  return p;
+}
+
+struct BatchGuard {
+  dfgpu_batch* b = nullptr;
+  ~BatchGuard() { if (b) dfgpu_batch_free(b); }
+};
+struct ResultGuard {
+  dfgpu_result* r = nullptr;
+  ~ResultGuard() { if (r) dfgpu_result_free(r); }
+};
+
+dfgpu_batch* upload(dfgpu_ctx* gpu, const RecordBatch& batch, const Pruned& p) {
+  std::vector<dfgpu_col> cols;
+  for (size_t c : p.cols) cols.push_back(batch.columns[c]->view());
+  if (cols.empty()) {
+    // a query that references no column still needs the row count: upload a 1-byte-per-row dummy? no —
+    // carry the row count through an empty Int8 column view of the first input column's length
+    fail(DFGPU_ERR_NOT_IMPLEMENTED, "queries that reference no column");
+  }
+  dfgpu_batch* out = nullptr;
+  GPU_CHECK(dfgpu_batch_upload(gpu, cols.data(), int(cols.size()), &out));
+  return out;
+}
+
+RecordBatch download(dfgpu_result* r, SchemaRef schema) {
+  RecordBatch out;
+  out.schema = std::move(schema);
+  int64_t nrows = 0;
+  int ncols = 0;
+  GPU_CHECK(dfgpu_result_shape(r, &nrows, &ncols));
+  out.num_rows = nrows;
+  for (int i = 0; i < ncols; i++) {
+    auto a = std::make_shared<Array>();
+    int32_t dt = 0;
+    int64_t nulls = 0, nbytes = 0;
+    GPU_CHECK(dfgpu_result_col_dtype(r, i, &dt));
+    GPU_CHECK(dfgpu_result_col_nulls(r, i, &nulls));
+    GPU_CHECK(dfgpu_result_col_bytes(r, i, &nbytes));
+    a->data_type = dt;
+    a->len = nrows;
+    a->null_count = nulls;
+    a->own_values.resize(size_t(nbytes > 0 ? nbytes : 1));
+    if (nulls > 0) a->own_validity.resize(size_t((nrows + 7) / 8));
+    if (dt == DFGPU_UTF8) a->own_offsets.resize(size_t(nrows + 1));
+    GPU_CHECK(dfgpu_result_copy_col(r, i, a->own_values.data(), nulls > 0 ? a->own_validity.data() : nullptr,
+                                    dt == DFGPU_UTF8 ? a->own_offsets.data() : nullptr));
+    a->values = a->own_values.data();
+    a->values_bytes = nbytes;
+    a->validity = nulls > 0 ? a->own_validity.data() : nullptr;
+    a->offsets = dt == DFGPU_UTF8 ? a->own_offsets.data() : nullptr;
+    out.columns.push_back(a);
+  }
+  return out;
+}
+
+}  // namespace
+
+std::string runtime_expr_name(const Expr& e, const Schema& s) {
+  switch (e.kind) {
+    case Expr::Column: return e.index < s.fields.size() ? s.fields[e.index].name : "?";
+    case Expr::Literal: return display_number(e.value);
+    case Expr::Cast: return e.left->kind == Expr::Column ? runtime_expr_name(*e.left, s) : "lit";
+    case Expr::BinaryExpr: return e.left->debug() + " " + operator_debug(e.op) + " " + e.right->debug();
+    case Expr::AggregateFunction: case Expr::ScalarFunction: return e.name;
+    default: return e.debug();
+  }
+}
+
+// ---- GPU relations ---------------------------------------------------------------------------------------
+GpuFilterProjectRelation::GpuFilterProjectRelation(dfgpu_ctx* gpu, RelationRef input, ExprRef predicate, std::vector<ExprRef> proj, SchemaRef schema)
+    : gpu_(gpu), input_(std::move(input)), predicate_(std::move(predicate)), proj_(std::move(proj)), schema_(std::move(schema)) {}
+
+std::optional<RecordBatch> GpuFilterProjectRelation::next() {
+  auto batch = input_->next();
+  if (!batch) return std::nullopt;
+  const Schema& in_schema = *input_->schema();
+  std::vector<ExprRef> all = proj_;
+  all.push_back(predicate_);
+  const bool emit_all = proj_.empty();  // FilterRelation alone gathers every input column (filter.rs:55-57)
+  Pruned pr = prune(all, batch->columns.size(), emit_all);
+  std::vector<dfgpu_insn> pred;
+  if (predicate_) lower(*predicate_, in_schema, pr.remap, pred);
+  std::vector<std::vector<dfgpu_insn>> progs;
+  if (emit_all) {
+    for (size_t c = 0; c < batch->columns.size(); c++) {
+      progs.emplace_back();
+      lower(*Expr::column(c), in_schema, pr.remap, progs.back());
+    }
+  } else {
+    for (auto& e : proj_) {
+      progs.emplace_back();
+      lower(*e, in_schema, pr.remap, progs.back());
+    }
+  }
+  std::vector<const dfgpu_insn*> pp;
+  std::vector<int> pl;
+  for (auto& p : progs) { pp.push_back(p.data()); pl.push_back(int(p.size())); }
+  BatchGuard b;
+  b.b = upload(gpu_, *batch, pr);
+  ResultGuard r;
+  GPU_CHECK(dfgpu_filter_project(gpu_, b.b, pred.data(), int(pred.size()), pp.data(), pl.data(), int(pp.size()), &r.r));
+  return download(r.r, schema_);
+}
+
+GpuAggregateRelation::GpuAggregateRelation(dfgpu_ctx* gpu, SchemaRef schema, RelationRef input, std::vector<ExprRef> group_expr,
+                                           std::vector<ExprRef> aggr_expr)
+    : gpu_(gpu), schema_(std::move(schema)), input_(std::move(input)), group_expr_(std::move(group_expr)), aggr_expr_(std::move(aggr_expr)) {}
+
+std::optional<RecordBatch> GpuAggregateRelation::next() {
+  if (end_of_results_) return std::nullopt;  // aggregate.rs:616-619
+  end_of_results_ = true;
+  const Schema& in_schema = *input_->schema();
+  std::vector<ExprRef> all = group_expr_;
+  std::vector<int> funcs;
+  for (auto& a : aggr_expr_) {
+    if (a->kind != Expr::AggregateFunction) fail(DFGPU_ERR_GENERAL, "Invalid aggregate expression");
+    if (a->args.size() != 1) fail(DFGPU_ERR_INTERNAL, "aggregate functions take exactly one argument (reference: assert_eq! at expression.rs:91)");
+    std::string n = a->name;
+    for (auto& c : n) c = char(tolower((unsigned char)c));
+    int f = n == "min" ? DFGPU_AGG_MIN : n == "max" ? DFGPU_AGG_MAX : n == "sum" ? DFGPU_AGG_SUM : n == "count" ? DFGPU_AGG_COUNT : 0;
+    if (!f) fail(DFGPU_ERR_GENERAL, "Unsupported aggregate function '" + a->name + "'");  // expression.rs:103-106
+    funcs.push_back(f);
+    all.push_back(a->args[0]);
+  }
+  dfgpu_aggstate* st = nullptr;
+  struct StGuard { dfgpu_aggstate** s; ~StGuard() { if (*s) dfgpu_aggregate_free(*s); } } sg{&st};
+  std::optional<Pruned> pr;
+  while (auto batch = input_->next()) {
+    if (!pr) {
+      pr = prune(all, batch->columns.size(), false);
+      std::vector<std::vector<dfgpu_insn>> kp(group_expr_.size()), ap(aggr_expr_.size());
+      std::vector<const dfgpu_insn*> kptr;
+      std::vector<int> klen;
+      for (size_t k = 0; k < group_expr_.size(); k++) {
+        lower(*group_expr_[k], in_schema, pr->remap, kp[k]);
+        kptr.push_back(kp[k].data());
+        klen.push_back(int(kp[k].size()));
+      }
+      std::vector<dfgpu_agg> aggs(aggr_expr_.size());
+      for (size_t a = 0; a < aggr_expr_.size(); a++) {
+        lower(*aggr_expr_[a]->args[0], in_schema, pr->remap, ap[a]);
+        aggs[a].func = funcs[a];
+        aggs[a].arg = ap[a].data();
+        aggs[a].arg_len = int(ap[a].size());
+        aggs[a].out_dtype = aggr_expr_[a]->data_type;
+        aggs[a]._pad = 0;
+      }
+      GPU_CHECK(dfgpu_aggregate_create(gpu_, kptr.data(), klen.data(), int(kptr.size()), aggs.data(), int(aggs.size()), 0, &st));
+    }
+    BatchGuard b;
+    b.b = upload(gpu_, *batch, *pr);
+    GPU_CHECK(dfgpu_aggregate_update(st, b.b));
+  }
+  if (!st) {
+    // empty input: no GROUP BY -> one row of nulls; GROUP BY -> empty batch
+    if (!group_expr_.empty()) {
+      RecordBatch out;
+      out.schema = schema_;
+      return out;
+    }
+    std::vector<std::vector<dfgpu_insn>> ap(aggr_expr_.size());
+    std::vector<dfgpu_agg> aggs(aggr_expr_.size());
+    for (size_t a = 0; a < aggr_expr_.size(); a++) {
+      dfgpu_insn in;
+      memset(&in, 0, sizeof(in));
+      in.op = DFGPU_OP_COL;
+      ap[a].push_back(in);
+      aggs[a].func = funcs[a];
+      aggs[a].arg = ap[a].data();
+      aggs[a].arg_len = 1;
+      aggs[a].out_dtype = aggr_expr_[a]->data_type;
+      aggs[a]._pad = 0;
+    }
+    GPU_CHECK(dfgpu_aggregate_create(gpu_, nullptr, nullptr, 0, aggs.data(), int(aggs.size()), 0, &st));
+  }
+  ResultGuard r;
+  GPU_CHECK(dfgpu_aggregate_finish(st, &r.r));
+  return download(r.r, schema_);
+}
+
+// ---- ExecutionContext ----------------------------------------------------------------------------------
+namespace {
+struct ContextSchemaProvider : SchemaProvider {  // context.rs:244-258
+  std::shared_ptr<std::map<std::string, DataSourceRef>> datasources;
+  SchemaRef get_table_meta(const std::string& name) const override {
+    auto it = datasources->find(name);
+    return it == datasources->end() ? nullptr : it->second->schema();
+  }
+  std::shared_ptr<FunctionMeta> get_function_meta(const std::string&) const override {
+    fail(DFGPU_ERR_NOT_IMPLEMENTED, "scalar functions are not registered with ExecutionContext (reference: unimplemented!() at context.rs:255-257)");
+  }
+};
+}  // namespace
+
+ExecutionContext::ExecutionContext(int device) : datasources_(std::make_shared<std::map<std::string, DataSourceRef>>()) {
+  GPU_CHECK(dfgpu_init(device, &gpu_));
+}
+ExecutionContext::~ExecutionContext() {
+  if (gpu_) dfgpu_shutdown(gpu_);
+}
+
+void ExecutionContext::register_datasource(const std::string& name, DataSourceRef ds) { (*datasources_)[name] = std::move(ds); }
+
+PlanRef ExecutionContext::plan(const std::string& sql) {
+  ASTRef ast = parse_sql(sql);
+  auto sp = std::make_shared<ContextSchemaProvider>();
+  sp->datasources = datasources_;
+  return SqlToRel(sp).sql_to_rel(ast);
+}
+
+RelationRef ExecutionContext::sql(const std::string& sql) { return execute(plan(sql)); }
+
+RelationRef ExecutionContext::execute(const PlanRef& plan) {
+  if (verbose) printf("Logical plan: %s\n", plan->debug().c_str());
+  switch (plan->kind) {
+    case LogicalPlan::TableScan: {
+      auto it = datasources_->find(plan->table_name);
+      if (it == datasources_->end()) fail(DFGPU_ERR_GENERAL, "No table registered as '" + plan->table_name + "'");
+      return std::make_shared<DataSourceRelation>(it->second);
+    }
+    case LogicalPlan::Selection: {  // context.rs:126-139 -> FilterRelation
+      RelationRef input_rel = execute(plan->input);
+      return std::make_shared<GpuFilterProjectRelation>(gpu_, input_rel, plan->expr[0], std::vector<ExprRef>{}, input_rel->schema());
+    }
+    case LogicalPlan::Projection: {  // context.rs:140-161 -> ProjectRelation (fused with a Selection below it)
+      ExprRef pred;
+      PlanRef src = plan->input;
+      if (src->kind == LogicalPlan::Selection) {
+        pred = src->expr[0];
+        src = src->input;
+      }
+      RelationRef input_rel = execute(src);
+      const Schema& in_schema = *input_rel->schema();
+      auto schema = std::make_shared<Schema>();
+      for (auto& e : plan->expr)  // projection.rs:52-57: (name, type, nullable = true)
+        schema->fields.push_back(Field{runtime_expr_name(*e, in_schema), e->get_type(in_schema), true});
+      return std::make_shared<GpuFilterProjectRelation>(gpu_, input_rel, pred, plan->expr, schema);
+    }
+    case LogicalPlan::Aggregate: {  // context.rs:162-192 -> AggregateRelation
+      RelationRef input_rel = execute(plan->input);
+      return std::make_shared<GpuAggregateRelation>(gpu_, plan->schema(), input_rel, plan->group_expr, plan->aggr_expr);
+    }
+    default:
+      fail(DFGPU_ERR_NOT_IMPLEMENTED, "Limit / Sort / EmptyRelation plans are not executable (reference: unimplemented!() at context.rs:194)");
+  }
+}
+
+}  // namespace dfhost

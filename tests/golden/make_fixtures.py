@@ -74,6 +74,14 @@ def main():
     with open(OUT, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", OUT)
+    # byte-for-byte copies of the three CSV data files the hot-path tests open (test DATA, not source),
+    # so CsvDataSource can be exercised on the GPU box where /root/reference does not exist
+    import shutil
+    data = os.path.join(os.path.dirname(OUT), "data")
+    os.makedirs(data, exist_ok=True)
+    for name in ["uk_cities.csv", "aggregate_test_1.csv", "aggregate_test_2.csv", "people.csv"]:
+        shutil.copyfile(os.path.join(REF, "test/data", name), os.path.join(data, name))
+    print("copied CSV fixtures to", data)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,127 @@
+"""End-to-end through the reference-shaped API: ExecutionContext.sql() -> Relation.next(), from the
+reference's own CSV fixtures (tests/sql.rs) and from in-memory Arrow batches.  GPU required."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from datafusion_archive_b200 import _abi as A
+from datafusion_archive_b200 import host, workloads
+from datafusion_archive_b200.expr import AggregateFunction, col, lit
+
+pytestmark = pytest.mark.gpu
+DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "data")
+
+
+@pytest.fixture()
+def ctx():
+    c = host.ExecutionContext(0)
+    yield c
+    c.close()
+
+
+def register_cities(ctx):  # tests/sql.rs:79-87
+    ctx.register_csv("cities", os.path.join(DATA, "uk_cities.csv"), [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 1024)
+
+
+def result_rows(rel):
+    rows = []
+    for batch in rel.collect():
+        rows.extend(zip(*batch))
+    return rows
+
+
+def test_csv_query_with_predicate_numeric_columns(ctx, golden, fmt_f64):
+    # tests/sql.rs:30-37 without the Utf8 column (GPU Utf8 gather: SURVEY §8f-3)
+    register_cities(ctx)
+    rel = ctx.sql("SELECT lat, lng, lat + lng FROM cities WHERE lat > 51.0 AND lat < 53")
+    assert rel.schema() == [("lat", A.FLOAT64), ("lng", A.FLOAT64), ("#1 Plus #2", A.FLOAT64)]  # projection.rs:52-57 names
+    got = ["%s\t%s\t%s" % tuple(fmt_f64(x) for x in r) for r in result_rows(rel)]
+    assert got == [l.split("\t", 1)[1] for l in golden["csv_query_with_predicate"]["expected"].splitlines()]
+    assert rel.next() is None
+
+
+def test_csv_query_cast(ctx, golden):
+    register_cities(ctx)
+    rows = result_rows(ctx.sql(golden["csv_query_cast"]["sql"]))
+    assert "".join("%d\n" % r[0] for r in rows) == golden["csv_query_cast"]["expected"]
+
+
+def test_csv_query_group_by_int_min_max(ctx, golden, fmt_f64):
+    ctx.register_csv("t1", os.path.join(DATA, "aggregate_test_1.csv"), [("a", A.INT32), ("b", A.FLOAT64)], 1024)
+    rows = result_rows(ctx.sql(golden["csv_query_group_by_int_min_max"]["sql"]))
+    got = sorted("%d\t%s\t%s\n" % (a, fmt_f64(b), fmt_f64(c)) for a, b, c in rows)
+    assert got == sorted(golden["csv_query_group_by_int_min_max"]["expected"].splitlines(True))
+
+
+def test_min_max_lat(ctx, golden):
+    register_cities(ctx)
+    rel = ctx.sql("SELECT MIN(lat), MAX(lat) FROM cities")
+    rows = result_rows(rel)
+    assert rows == [(golden["min_lat"], golden["max_lat"])]
+    assert rel.next() is None  # AggregateRelation is one-shot (aggregate.rs:616-619)
+
+
+def test_small_batches_match_single_batch(ctx):
+    ctx.register_csv("c7", os.path.join(DATA, "uk_cities.csv"), [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 7)
+    ctx.register_csv("c1024", os.path.join(DATA, "uk_cities.csv"), [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 1024)
+    q = "SELECT lat * lng, lng FROM %s WHERE lng < 0 OR lat > 55.5"
+    a, b = result_rows(ctx.sql(q % "c7")), result_rows(ctx.sql(q % "c1024"))
+    assert a == b and len(a) > 0
+    q = "SELECT SUM(lat), COUNT(lat), MIN(lng) FROM %s"
+    a, b = result_rows(ctx.sql(q % "c7")), result_rows(ctx.sql(q % "c1024"))
+    assert a[0][1] == b[0][1] == 36 and a[0][2] == b[0][2]
+    assert abs(a[0][0] - b[0][0]) <= 1e-9 * abs(b[0][0])
+
+
+def test_memory_tables_baseline_queries(ctx):
+    n = 300_000
+    arrays, pred, proj = workloads.c3(n)
+    ctx.register_memory("t", list(zip("abcd", arrays)))
+    got = ctx.sql("SELECT a+b, a*b FROM t WHERE b<a").collect()
+    assert len(got) == 1
+    exp = O.filter_project(arrays, pred, proj)
+    for g, e in zip(got[0], exp):
+        assert np.array_equal(g.view(np.uint8), e.view(np.uint8))
+    got = ctx.sql("SELECT a FROM t WHERE a > 0.5").collect()[0][0]
+    assert np.array_equal(got, arrays[0][arrays[0] > 0.5])
+    # batched source: output is the concatenation of per-batch outputs
+    ctx.register_memory("tb", list(zip("abcd", arrays)), batch_size=65536)
+    parts = ctx.sql("SELECT a FROM tb WHERE a > 0.5").collect()
+    assert len(parts) == 5 and np.array_equal(np.concatenate([p[0] for p in parts]), got)
+
+    arrays4, keys, aggs, _ = workloads.c4(n, nkeys=5000)
+    ctx.register_memory("g", [("k", arrays4[0]), ("v", arrays4[1])], batch_size=100_000)
+    rel = ctx.sql("SELECT k, SUM(v), COUNT(v) FROM g GROUP BY k")
+    assert [f[0] for f in rel.schema()] == ["k", "SUM", "COUNT"]
+    k, s, c = rel.collect()[0]
+    exp = O.aggregate(arrays4, keys, aggs)
+    o1, o2 = np.argsort(k), np.argsort(exp[0])
+    assert np.array_equal(k[o1], exp[0][o2]) and np.array_equal(c[o1], exp[2][o2]) and c.dtype == np.uint64
+    np.testing.assert_allclose(s[o1], exp[1][o2], rtol=1e-9)
+    # a WHERE below an aggregate: Aggregate(Selection(TableScan))
+    k2, mx = ctx.sql("SELECT k, MAX(v) FROM g WHERE v < 0.25 GROUP BY k").collect()[0]
+    m = arrays4[1] < 0.25
+    e2 = O.aggregate([arrays4[0][m], arrays4[1][m]], keys, [AggregateFunction("max", col(1))])
+    o1, o2 = np.argsort(k2), np.argsort(e2[0])
+    assert np.array_equal(k2[o1], e2[0][o2]) and np.array_equal(mx[o1], e2[1][o2])
+
+
+def test_error_mapping(ctx):
+    register_cities(ctx)
+    for sql, code, msg in [
+        ("SELECT lat FROM nowhere", A.ERR_GENERAL, "no schema found for table nowhere"),
+        ("SELECT lat FROM cities ORDER BY lat", A.ERR_NOT_IMPLEMENTED, "unimplemented!()"),
+        ("SELECT lat FROM cities LIMIT 3", A.ERR_NOT_IMPLEMENTED, "unimplemented!()"),
+        ("SELECT lat % 2 FROM cities", A.ERR_EXECUTION, "operator: Modulus"),
+        ("SELECT lat FROM cities WHERE lat IS NULL", A.ERR_EXECUTION, "expression #1 IS NULL"),
+        ("SELECT lat / 0 FROM cities", A.ERR_ARROW, "DivideByZero"),
+        ("SELECT lat FROM cities WHERE lat + 1", A.ERR_EXECUTION, "Filter expression did not evaluate to boolean"),
+        ("SELECT lat, SUM(lng) FROM cities GROUP BY lat", A.ERR_EXECUTION, "Unsupported GROUP BY data type"),
+    ]:
+        with pytest.raises(host.ExecutionError) as e:
+            rel = ctx.sql(sql)
+            rel.next()
+        assert e.value.code == code, (sql, e.value.msg)
+        assert msg in e.value.msg, (sql, e.value.msg)
