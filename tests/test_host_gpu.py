@@ -64,15 +64,21 @@ def test_min_max_lat(ctx, golden):
 
 
 def test_small_batches_match_single_batch(ctx):
-    ctx.register_csv("c7", os.path.join(DATA, "uk_cities.csv"), [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 7)
-    ctx.register_csv("c1024", os.path.join(DATA, "uk_cities.csv"), [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 1024)
+    # a CsvDataSource is a one-pass reader shared by reference (Rc<RefCell<DataSource>>, context.rs:100-102):
+    # every query gets its own registration, as in the reference's tests
+    fields = [("city", A.UTF8), ("lat", A.FLOAT64), ("lng", A.FLOAT64)]
+    for name, bs in [("c7", 7), ("c1024", 1024), ("d7", 7), ("d1024", 1024)]:
+        ctx.register_csv(name, os.path.join(DATA, "uk_cities.csv"), fields, bs)
     q = "SELECT lat * lng, lng FROM %s WHERE lng < 0 OR lat > 55.5"
     a, b = result_rows(ctx.sql(q % "c7")), result_rows(ctx.sql(q % "c1024"))
     assert a == b and len(a) > 0
     q = "SELECT SUM(lat), COUNT(lat), MIN(lng) FROM %s"
-    a, b = result_rows(ctx.sql(q % "c7")), result_rows(ctx.sql(q % "c1024"))
+    a, b = result_rows(ctx.sql(q % "d7")), result_rows(ctx.sql(q % "d1024"))
     assert a[0][1] == b[0][1] == 36 and a[0][2] == b[0][2]
     assert abs(a[0][0] - b[0][0]) <= 1e-9 * abs(b[0][0])
+    # the exhausted reader yields nothing on a second query: no GROUP BY -> one row of nulls (aggregate.rs:641-643)
+    vals, mask = ctx.sql("SELECT SUM(lat) FROM d7").collect()[0][0]
+    assert len(vals) == 1 and not mask[0]
 
 
 def test_memory_tables_baseline_queries(ctx):
@@ -84,6 +90,7 @@ def test_memory_tables_baseline_queries(ctx):
     exp = O.filter_project(arrays, pred, proj)
     for g, e in zip(got[0], exp):
         assert np.array_equal(g.view(np.uint8), e.view(np.uint8))
+    ctx.register_memory("t", list(zip("abcd", arrays)))  # data sources are one-pass (see above)
     got = ctx.sql("SELECT a FROM t WHERE a > 0.5").collect()[0][0]
     assert np.array_equal(got, arrays[0][arrays[0] > 0.5])
     # batched source: output is the concatenation of per-batch outputs
@@ -101,6 +108,7 @@ def test_memory_tables_baseline_queries(ctx):
     assert np.array_equal(k[o1], exp[0][o2]) and np.array_equal(c[o1], exp[2][o2]) and c.dtype == np.uint64
     np.testing.assert_allclose(s[o1], exp[1][o2], rtol=1e-9)
     # a WHERE below an aggregate: Aggregate(Selection(TableScan))
+    ctx.register_memory("g", [("k", arrays4[0]), ("v", arrays4[1])], batch_size=100_000)
     k2, mx = ctx.sql("SELECT k, MAX(v) FROM g WHERE v < 0.25 GROUP BY k").collect()[0]
     m = arrays4[1] < 0.25
     e2 = O.aggregate([arrays4[0][m], arrays4[1][m]], keys, [AggregateFunction("max", col(1))])
@@ -120,6 +128,7 @@ def test_error_mapping(ctx):
         ("SELECT lat FROM cities WHERE lat + 1", A.ERR_EXECUTION, "Filter expression did not evaluate to boolean"),
         ("SELECT lat, SUM(lng) FROM cities GROUP BY lat", A.ERR_EXECUTION, "Unsupported GROUP BY data type"),
     ]:
+        register_cities(ctx)  # fresh one-pass reader per query
         with pytest.raises(host.ExecutionError) as e:
             rel = ctx.sql(sql)
             rel.next()
