@@ -68,11 +68,26 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-// 1-D bulk async copy global -> shared, completion reported to an mbarrier (TMA engine; UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+// 1-D bulk async copy global -> shared, completion reported to an mbarrier (TMA engine; UBLKCP),
+// with an L2 eviction-priority hint: the predicate stream marks bytes that the projection stream
+// will re-read LAG tiles later as evict_last; the projection stream (and bytes read once) use
+// evict_first so they do not push the pending re-reads out of L2.
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                            unsigned long long policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 
 struct TmaShared {
@@ -89,8 +104,9 @@ static_assert(sizeof(TmaShared) <= TM_HDR_BYTES, "shared header too large");
 
 // One producer warp: stream the `ncols` columns listed in `slots` of every tile this CTA owns into
 // a ring of S stages.
-__device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, const int* col_off, unsigned char* ring, int S,
-                                              int stage_bytes, unsigned long long* full, unsigned long long* empty, int lane) {
+__device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, const int* col_off, const int* reread_off, unsigned char* ring,
+                                              int S, int stage_bytes, unsigned long long* full, unsigned long long* empty, int lane) {
+  const unsigned long long keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
   int s = 0;
   unsigned ph = 1;  // first pass over the ring returns immediately
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
@@ -107,7 +123,7 @@ __device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, 
         for (int c = 0; c < p.ps.ncols; c++)
           if (col_off[c] >= 0)
             tma_load_1d(dst + col_off[c], (const unsigned char*)p.ps.cols[c].ptr + row0 * p.col_w[c], (unsigned)(tile_rows * p.col_w[c]),
-                        &full[s]);
+                        &full[s], (reread_off && reread_off[c] >= 0) ? keep : stream);
       }
     } else {
       // ragged last tile: sizes need not be 16-byte multiples, so the warp copies it by hand
@@ -183,12 +199,12 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
 
   if (warp == TM_CWARPS) {
     // ================================ producer A: predicate columns ============================
-    if (p.has_pred) producer_loop(p, TILE, p.col_offA, ringA, SA, p.stage_bytesA, sh.fullA, sh.emptyA, lane);
+    if (p.has_pred) producer_loop(p, TILE, p.col_offA, p.col_offB, ringA, SA, p.stage_bytesA, sh.fullA, sh.emptyA, lane);
   } else if (warp == TM_CWARPS + 1) {
     // ================================ producer B: projection columns ===========================
     // Runs as far ahead as ring B allows; the consumers reach these tiles LAG iterations after the
     // predicate pass touched the same rows, so the bytes are L2 hits.
-    producer_loop(p, TILE, p.col_offB, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
+    producer_loop(p, TILE, p.col_offB, nullptr, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
   } else if (warp >= TM_CWARPS + 2) {
     // ================================ scan warps ================================================
     if (!p.has_pred) return;  // nothing is dropped: output positions are the row numbers
@@ -518,7 +534,18 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   p.nstagesA = offA ? S : 0;
   p.nstagesB = S;
   if (!p.has_pred) p.nstagesB = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / offB);
-  p.lag = p.has_pred ? std::min(TM_MAX_LAG, 64 / K - 1) : 0;
+  // lag: as large as the flag shift register allows (K bits per tile in 64 bits), but the bytes the
+  // projection stream will re-read (lag x grid x stage B) must still be in L2 when it gets there
+  p.lag = 0;
+  if (p.has_pred) {
+    const long long l2_budget = 40ll << 20;
+    const long long per_tile = (long long)std::min(ctx->sm_count, TM_MAX_GRID) * offB;
+    p.lag = (int)std::min<long long>(std::min(TM_MAX_LAG, 64 / K - 1), std::max<long long>(4, l2_budget / per_tile));
+  }
+  if (const char* e = getenv("DFGPU_FP_LAG")) {  // experiment knob
+    const int l = atoi(e);
+    if (p.has_pred && l >= 1 && l <= std::min(TM_MAX_LAG, 64 / K - 1)) p.lag = l;
+  }
   p.ntiles = int((p.nrows + tile - 1) / tile);
   const size_t smem = TM_HDR_BYTES + (size_t)p.nstagesA * p.stage_bytesA + (size_t)p.nstagesB * p.stage_bytesB;
   const int d = p.ps.max_depth;

@@ -1,0 +1,85 @@
+"""Worker for the world_size>1 tests (launched by torch.distributed.run).
+  mode gloo : CPU.  Each rank computes its shard with the ORACLE (test infrastructure), partials are
+              exchanged over gloo, merged with parallel.merge_partials, checked against the oracle on
+              the full data.  Exercises the partitioning + merge algebra without a GPU.
+  mode nccl : GPUs.  Each rank drives its own B200 through the C ABI with a communicator attached;
+              every rank must end with the global result (dfgpu_aggregate_finish merges over NCCL).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import oracle_lib as O  # noqa: E402
+from datafusion_archive_b200 import _abi as A, parallel, workloads  # noqa: E402
+from datafusion_archive_b200.expr import AggregateFunction, col  # noqa: E402
+
+
+def sort_by_key(cols):
+    o = np.argsort(cols[0], kind="stable")
+    return [c[o] for c in cols]
+
+
+def main():
+    mode = sys.argv[1]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    n = 400_000
+    arrays, keys, aggs, _ = workloads.c5(n, nkeys=3000)
+    aggs = aggs + [AggregateFunction("count", col(1))]
+    funcs = [A.AGG_MIN, A.AGG_MAX, A.AGG_SUM, A.AGG_COUNT]
+    full = sort_by_key(O.aggregate(arrays, keys, aggs))
+    mine = parallel.shard(arrays, rank, world)
+    fa, fpred, fproj = workloads.c2(n)
+    fmine = parallel.shard(fa, rank, world)
+    if mode == "gloo":
+        dist.init_process_group("gloo")
+        part = O.aggregate(mine, keys, aggs)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, part)
+        merged = parallel.merge_partials(gathered, funcs)
+        fpart = O.filter_project(fmine, fpred, fproj)
+        fg = [None] * world
+        dist.all_gather_object(fg, fpart)
+        fout = parallel.concat_in_rank_order(fg)
+        # no GROUP BY: scalars combine with the same algebra
+        spart = O.aggregate(mine, [], aggs)
+        sg = [None] * world
+        dist.all_gather_object(sg, [np.zeros(1, dtype=np.int64)] + [np.asarray(c) for c in spart])
+        smerged = parallel.merge_partials(sg, funcs)[1:]
+    else:
+        from datafusion_archive_b200 import engine
+        local = int(os.environ.get("LOCAL_RANK", rank))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ctx = engine.GpuContext(local)
+        uid = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+        b = ctx.upload(mine)
+        merged = sort_by_key(ctx.aggregate(b, keys, aggs).columns())  # every rank: the GLOBAL result
+        smerged = ctx.aggregate(b, [], aggs).columns()
+        fb = ctx.upload(fmine)
+        fpart = ctx.filter_project(fb, fpred, fproj).columns()
+        fg = [None] * world
+        dist.all_gather_object(fg, fpart)
+        fout = parallel.concat_in_rank_order(fg)
+    assert np.array_equal(merged[0], full[0]), "keys differ"
+    assert np.array_equal(merged[1], full[1]) and np.array_equal(merged[2], full[2]), "min/max differ"
+    np.testing.assert_allclose(merged[3], full[3], rtol=1e-9)
+    assert np.array_equal(merged[4], full[4]), "counts differ"
+    sfull = O.aggregate(arrays, [], aggs)
+    assert smerged[0][0] == sfull[0][0] and smerged[1][0] == sfull[1][0] and smerged[3][0] == sfull[3][0] == n
+    assert abs(smerged[2][0] - sfull[2][0]) <= 1e-9 * abs(sfull[2][0])
+    assert np.array_equal(fout[0], fa[0][fa[0] > 0.5]), "rank-ordered concatenation is not the global filter output"
+    dist.barrier()
+    if rank == 0:
+        print("MP_OK mode=%s world=%d groups=%d" % (mode, world, len(merged[0])))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
