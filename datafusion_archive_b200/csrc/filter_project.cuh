@@ -46,6 +46,7 @@ struct FPParams {
   int stage_bytesA, stage_bytesB;
   int nstagesA, nstagesB;
   int lag;  // tiles between the predicate pass and the projection pass
+  int single_ring;  // 1: one ring holds the union of the columns; the projection pass reads the SAME staged tile
   // "fast shapes": single-operation Float64 programs are recognised on the host and executed by
   // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).
   //   predicate : chain of (COL cmp COL | COL cmp IMM) joined by AND / OR

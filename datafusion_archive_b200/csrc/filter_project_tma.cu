@@ -11,8 +11,8 @@
 //   16 consumer warps   : phase 1 = predicate of tile it over ring A -> K flag bits per lane, kept in
 //                         a 64-bit shift register; phase 2 = projections of tile it-LAG over ring B,
 //                         selected rows stored at their compacted global position
-//   4 scan warps        : turn the per-warp counts of a tile into global output offsets, 4 waves per
-//                         warp at a time (16 cross-CTA gathers in flight per SM)
+//   2 scan warps        : turn the per-warp counts of a tile into global output offsets, 4 waves per
+//                         warp at a time (8 cross-CTA gathers in flight per SM)
 //
 // Why the lag: order-preserving compaction needs, per tile, the number of selected rows in ALL
 // earlier tiles.  Under a bandwidth-saturating stream every dependent global round trip costs
@@ -21,10 +21,13 @@
 // only produces 1 bit per row, runs LAG tiles ahead; by the time the projection pass reaches a
 // tile its offset has long been resolved, and the tile's bytes come back from L2, not HBM.
 //
+// The lag must be >= TM_BATCH - 1: a scan warp waits for the counts of a whole batch of waves, and the
+// consumers only reach the projection pass of wave w after the predicate pass of wave w + LAG.
+//
 // Offsets: every scan warp publishes its tile's count, then GATHERS the counts of all G tiles of
 // its wave with one batch of parallel loads: offset = base + sum(counts of lower CTAs); base
 // advances by the wave total, computed redundantly by every CTA (nothing is forwarded between
-// waves through memory).  The 4 scan warps take waves round-robin so 4 gathers are in flight; the
+// waves through memory).  The scan warps take batches of waves round-robin; the
 // running base is handed from wave to wave through shared memory.
 //
 // Nothing in the CTA executes __syncthreads in the steady state; all hand-offs are mbarriers.
@@ -34,7 +37,7 @@
 namespace dfgpu {
 
 constexpr int TM_CWARPS = 16;  // consumer warps
-constexpr int TM_SWARPS = 4;   // scan warps
+constexpr int TM_SWARPS = 2;   // scan warps (2 x TM_BATCH gathers in flight; 20 warps leave 96 registers per thread)
 constexpr int TM_BATCH = 4;    // waves per scan-warp batch
 constexpr int TM_WARPS = TM_CWARPS + 2 + TM_SWARPS;
 constexpr int TM_THREADS = TM_WARPS * 32;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
     // ================================ producer B: projection columns ===========================
     // Runs as far ahead as ring B allows; the consumers reach these tiles LAG iterations after the
     // predicate pass touched the same rows, so the bytes are L2 hits.
-    producer_loop(p, TILE, p.col_offB, nullptr, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
+    if (!p.single_ring) producer_loop(p, TILE, p.col_offB, nullptr, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
   } else if (warp >= TM_CWARPS + 2) {
     // ================================ scan warps ================================================
     if (!p.has_pred) return;  // nothing is dropped: output positions are the row numbers
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       for (int k = 0; k < K; k++) cnt += __popc(__ballot_sync(0xffffffffu, (flags >> k) & 1u));
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&sh.emptyA[s]);  // this warp is done reading the stage
+        if (!p.single_ring) mbar_arrive(&sh.emptyA[s]);  // this warp is done reading the stage
         sh.s_cnt[it % TM_RING][warp] = cnt;
         mbar_arrive(&sh.cnt_ready[it % TM_RING]);
       }
@@ -351,9 +354,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       } else {
         base = (unsigned long long)tile * TILE + (unsigned long long)warp * 32 * K;
       }
-      mbar_wait(&sh.fullB[s], ph);
       StagedTile<K> src;
-      src.stage = ringB + (size_t)s * p.stage_bytesB;
+      if (p.single_ring) {
+        // the tile is still resident in ring A (held since the predicate pass): no second load
+        src.stage = ringA + (size_t)s * p.stage_bytesA;
+      } else {
+        mbar_wait(&sh.fullB[s], ph);
+        src.stage = ringB + (size_t)s * p.stage_bytesB;
+      }
       src.col_off = p.col_offB;
       src.lrow0 = warp * 32 * K + lane;
       src.valid = flags;  // a zero divisor only matters on rows that survive the filter
@@ -416,7 +424,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh.emptyB[s]);
+      if (lane == 0) mbar_arrive(p.single_ring ? &sh.emptyA[s] : &sh.emptyB[s]);
     };
 
     int nloc = 0;
@@ -466,7 +474,7 @@ static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   auto kern = k_filter_project_tma<DEPTH, K, F64ONLY>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + TM_HDR_BYTES));
+    DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 16384 + TM_HDR_BYTES));
     configured = true;
   }
   long long grid = std::min(ctx->sm_count, TM_MAX_GRID);  // one persistent CTA per SM
@@ -505,21 +513,43 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   }
   // projections of literals only, or a predicate over literals only: leave to the direct kernel
   if (rowB == 0 || (p.has_pred && rowA == 0)) return false;
-  // rows per lane K in {8,4,2}: the biggest tile that still gives both rings 3 stages.  Measured on
-  // B200 (profiles/r01_microbench_fp.txt): per-tile fixed costs (barrier hand-offs, offset gather)
-  // outweigh deeper prefetch, so bigger tiles with 3 stages beat smaller tiles with 6.
+  // Two layouts.
+  //  single ring: one ring holds the UNION of the referenced columns; a tile stays staged from its
+  //    predicate pass until its projection pass LAG tiles later (no second load).  Needs LAG + 2 stages,
+  //    so it is used when the union is narrow enough for >= 6 stages of a >= 1024-row tile.
+  //  dual ring: ring A = predicate columns, ring B = projection columns re-read LAG tiles later from
+  //    L2 (evict_last / evict_first hints).  Any width; the lag can be long.
+  int rowU = 0;
+  for (int c = 0; c < p.ps.ncols; c++)
+    if (inA[c] || inB[c]) rowU += p.col_w[c];
+  const char* mode = getenv("DFGPU_FP_MODE");  // experiment knob: single | dual
   int K = 0;
-  for (int k : {8, 4, 2}) {
-    if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
-    const long long tile = (long long)TM_CWARPS * 32 * k;
-    if (tile * (rowA + rowB) * 3 <= TM_SMEM_BUDGET) { K = k; break; }
+  p.single_ring = 0;
+  if (p.has_pred && mode && std::string(mode) == "single") {  // measured slower than dual on B200 (profiles/r01_history.md): opt-in only
+    for (int k : {8, 4, 2}) {
+      if (k == 8 && p.ps.max_depth > 2) continue;
+      const long long tile = (long long)TM_CWARPS * 32 * k;
+      if (tile * rowU * 6 <= TM_SMEM_BUDGET + 16384) { K = k; p.single_ring = 1; break; }
+    }
+  }
+  if (!p.single_ring) {
+    // rows per lane K in {8,4,2}: the biggest tile that still gives both rings 3 stages.  Measured on
+    // B200 (profiles/r01_microbench_fp.txt): per-tile fixed costs (barrier hand-offs, offset gather)
+    // outweigh deeper prefetch, so bigger tiles with few stages beat smaller tiles with many.
+    for (int k : {8, 4, 2}) {
+      if (k == 8 && p.ps.max_depth > 2) continue;  // deep register stacks spill at 8 rows per lane
+      const long long tile = (long long)TM_CWARPS * 32 * k;
+      if (tile * (rowA + rowB) * 3 <= TM_SMEM_BUDGET) { K = k; break; }
+    }
   }
   if (const char* e = getenv("DFGPU_FP_K")) {  // experiment knob
     const int k = atoi(e);
-    if ((k == 8 || k == 4 || k == 2) && (long long)TM_CWARPS * 32 * k * (rowA + rowB) * 2 <= TM_SMEM_BUDGET && !(k == 8 && p.ps.max_depth > 2)) K = k;
+    if (!p.single_ring && (k == 8 || k == 4 || k == 2) && (long long)TM_CWARPS * 32 * k * (rowA + rowB) * 2 <= TM_SMEM_BUDGET && !(k == 8 && p.ps.max_depth > 2)) K = k;
   }
   if (!K) return false;
   const int tile = TM_CWARPS * 32 * K;
+  if (p.single_ring)
+    for (int c = 0; c < p.ps.ncols; c++) inA[c] = inB[c] = inA[c] || inB[c];
   int offA = 0, offB = 0;
   for (int c = 0; c < p.ps.ncols; c++) {
     // tile is a multiple of 512 rows: every column slice stays 128-B aligned
@@ -530,21 +560,41 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   }
   p.stage_bytesA = offA;
   p.stage_bytesB = offB;
-  const int S = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / (offA + offB));
-  p.nstagesA = offA ? S : 0;
-  p.nstagesB = S;
-  if (!p.has_pred) p.nstagesB = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / offB);
-  // lag: as large as the flag shift register allows (K bits per tile in 64 bits), but the bytes the
-  // projection stream will re-read (lag x grid x stage B) must still be in L2 when it gets there
-  p.lag = 0;
-  if (p.has_pred) {
-    const long long l2_budget = 40ll << 20;
-    const long long per_tile = (long long)std::min(ctx->sm_count, TM_MAX_GRID) * offB;
-    p.lag = (int)std::min<long long>(std::min(TM_MAX_LAG, 64 / K - 1), std::max<long long>(4, l2_budget / per_tile));
-  }
-  if (const char* e = getenv("DFGPU_FP_LAG")) {  // experiment knob
-    const int l = atoi(e);
-    if (p.has_pred && l >= 1 && l <= std::min(TM_MAX_LAG, 64 / K - 1)) p.lag = l;
+  if (p.single_ring) {
+    p.nstagesA = std::min(TM_MAX_STAGES, (TM_SMEM_BUDGET + 16384) / offA);
+    p.nstagesB = p.nstagesA;  // the projection pass walks the same ring
+    p.stage_bytesB = 0;
+    p.lag = p.nstagesA - 3;  // LAG+1 stages are held by the consumers, 2 are prefetch depth
+    if (p.lag < TM_BATCH - 1) return false;
+    if (const char* e = getenv("DFGPU_FP_LAG")) {
+      const int l = atoi(e);
+      if (l >= TM_BATCH - 1 && l <= p.nstagesA - 2) p.lag = l;
+    }
+  } else {
+    const int S = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / (offA + offB));
+    p.nstagesA = offA ? S : 0;
+    p.nstagesB = S;
+    if (!p.has_pred) p.nstagesB = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / offB);
+    if (const char* e = getenv("DFGPU_FP_STAGES")) {  // experiment knob: "A,B"
+      int sa = 0, sb = 0;
+      if (sscanf(e, "%d,%d", &sa, &sb) == 2 && sa >= 1 && sb >= 1 && sa <= TM_MAX_STAGES && sb <= TM_MAX_STAGES &&
+          (long long)sa * offA + (long long)sb * offB <= TM_SMEM_BUDGET + 16384 && p.has_pred) {
+        p.nstagesA = sa;
+        p.nstagesB = sb;
+      }
+    }
+    // lag: as large as the flag shift register allows (K bits per tile in 64 bits), but the bytes the
+    // projection stream will re-read (lag x grid x stage B) must still be in L2 when it gets there
+    p.lag = 0;
+    if (p.has_pred) {
+      const long long l2_budget = 40ll << 20;
+      const long long per_tile = (long long)std::min(ctx->sm_count, TM_MAX_GRID) * offB;
+      p.lag = (int)std::min<long long>(std::min(TM_MAX_LAG, 64 / K - 1), std::max<long long>(4, l2_budget / per_tile));
+    }
+    if (const char* e = getenv("DFGPU_FP_LAG")) {  // experiment knob
+      const int l = atoi(e);
+      if (p.has_pred && l >= TM_BATCH - 1 && l <= std::min(TM_MAX_LAG, 64 / K - 1)) p.lag = l;
+    }
   }
   p.ntiles = int((p.nrows + tile - 1) / tile);
   const size_t smem = TM_HDR_BYTES + (size_t)p.nstagesA * p.stage_bytesA + (size_t)p.nstagesB * p.stage_bytesB;
