@@ -225,6 +225,20 @@ int ProgramBuilder::add(const dfgpu_insn* p, int n, const char* what) {
   return int(progs_.size()) - 1;
 }
 
+int ProgramBuilder::add_rowid() {
+  CompiledProgram cp;
+  DevInsn di;
+  memset(&di, 0, sizeof(di));
+  di.op = V_PUSH_ROWID;
+  di.dtype = DFGPU_UINT64;
+  di.mtype = MT_U;
+  cp.code.push_back(di);
+  cp.out_dtype = DFGPU_UINT64;
+  cp.max_depth = 1;
+  progs_.push_back(std::move(cp));
+  return int(progs_.size()) - 1;
+}
+
 void ProgramBuilder::finish(ProgramSet* out) const {
   memset(out, 0, sizeof(*out));
   if (int(progs_.size()) > kMaxProgs)

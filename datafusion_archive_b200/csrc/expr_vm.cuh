@@ -15,7 +15,7 @@ namespace dfgpu {
 
 enum MType : uint8_t { MT_NONE = 0, MT_F64 = 1, MT_F32 = 2, MT_I = 3, MT_U = 4, MT_BOOL = 5 };
 enum VOp : uint8_t {
-  V_PUSH_COL = 0, V_PUSH_IMM, V_CAST,
+  V_PUSH_COL = 0, V_PUSH_IMM, V_PUSH_ROWID /* global row number (gather index of variable-width columns) */, V_CAST,
   V_ADD, V_SUB, V_MUL, V_DIV,
   V_EQ, V_NE, V_LT, V_LE, V_GT, V_GE,
   V_AND, V_OR
@@ -67,6 +67,8 @@ class ProgramBuilder {
   explicit ProgramBuilder(const dfgpu_batch* batch) : batch_(batch) {}
   // Type-check + lower one postfix program; appends to the set and returns its index.
   int add(const dfgpu_insn* p, int n, const char* what);
+  // Program yielding the global row number (UInt64): the gather index for variable-width columns.
+  int add_rowid();
   int out_dtype(int prog) const { return progs_[size_t(prog)].out_dtype; }
   const CompiledProgram& prog(int i) const { return progs_[size_t(i)]; }
   int nprogs() const { return int(progs_.size()); }
@@ -140,6 +142,7 @@ struct GlobalRows {
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
   }
+  __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)rows[r]; }
 };
 template <int R>
 struct StagedTile {
@@ -147,9 +150,11 @@ struct StagedTile {
   const int* col_off;
   int lrow0;
   unsigned valid;
+  long long row0;  // global row number of (tile, lrow0)
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return load_elem_generic(stage + col_off[slot], ps.cols[slot].dtype, lrow0 + r * 32);
   }
+  __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)(row0 + r * 32); }
 };
 
 __device__ __forceinline__ void store_elem(void* p, int dtype, long long idx, unsigned long long v) {
@@ -243,7 +248,7 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
     const int dt = ps.insn[pc].dtype;
     const int slot = ps.insn[pc].slot;
     const unsigned long long imm = ps.insn[pc].imm;
-    if (op <= V_PUSH_IMM) {
+    if (op <= V_PUSH_ROWID) {
       // push
 #pragma unroll
       for (int d = DEPTH - 1; d > 0; d--)
@@ -252,6 +257,9 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
       if (op == V_PUSH_IMM) {
 #pragma unroll
         for (int r = 0; r < R; r++) st[0][r] = imm;
+      } else if (op == V_PUSH_ROWID) {
+#pragma unroll
+        for (int r = 0; r < R; r++) st[0][r] = src.rowid(r);
       } else {
 #pragma unroll
         for (int r = 0; r < R; r++) st[0][r] = src.load(ps, slot, r);

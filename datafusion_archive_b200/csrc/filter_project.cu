@@ -167,6 +167,9 @@ static void launch_fp(dfgpu_ctx* ctx, const FPParams& p) {
 
 }  // namespace dfgpu
 
+namespace dfgpu {
+void gather_utf8(dfgpu_ctx* ctx, const DevColumn& src, const unsigned long long* d_idx, long long nsel, DevColumn* out);
+}
 using namespace dfgpu;
 
 extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_insn* pred, int pred_len,
@@ -201,12 +204,29 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       proj = pptr.data();
       proj_len = plen.data();
     }
+    // Projections that are a plain Utf8 column are gathered by row number after the fused kernel
+    // (utf8_gather.cu); everything else is evaluated inside it.
+    std::vector<int> out_kind;  // per output column: >= 0 kernel program slot, -1 - c = Utf8 gather of input column c
+    int nkern = 0;
+    bool any_utf8 = false;
     for (int i = 0; i < nproj; i++) {
+      if (proj_len[i] == 1 && proj[i][0].op == DFGPU_OP_COL && proj[i][0].col >= 0 && size_t(proj[i][0].col) < batch->cols.size() &&
+          batch->cols[size_t(proj[i][0].col)].dtype == DFGPU_UTF8) {
+        out_kind.push_back(-1 - proj[i][0].col);
+        any_utf8 = true;
+        continue;
+      }
       int pi = pb.add(proj[i], proj_len[i], "projection");
       int dt = pb.out_dtype(pi);
       if (!is_numeric(dt))
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("filter/projection output of type ") + dtype_name(dt) +
                                             " is not supported on the GPU path yet");
+      out_kind.push_back(nkern++);
+    }
+    int rowid_slot = -1;
+    if (any_utf8) {
+      pb.add_rowid();
+      rowid_slot = nkern++;
     }
     // columns referenced anywhere must be null-free and fixed width for now
     FPParams p;
@@ -222,22 +242,46 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     auto res = std::make_unique<dfgpu_result>();
     res->ctx = ctx;
     const long long n = batch->nrows;
+    // kernel outputs (worst case n rows each); the row-number column is scratch, not a result column
+    dfgpu_result scratch;  // RAII for the row-number buffer
+    scratch.ctx = ctx;
+    std::vector<void*> kern_out(size_t(nkern), nullptr);
     for (int i = 0; i < nproj; i++) {
       DevColumn c;
-      c.dtype = pb.out_dtype(i + has_pred);
-      c.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(c.dtype));
-      c.values = ctx->alloc(c.values_bytes);
+      if (out_kind[size_t(i)] >= 0) {
+        c.dtype = pb.out_dtype(out_kind[size_t(i)] + has_pred);
+        c.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(c.dtype));
+        c.values = ctx->alloc(c.values_bytes);
+        kern_out[size_t(out_kind[size_t(i)])] = c.values;
+      } else {
+        c.dtype = DFGPU_UTF8;  // filled by the gather below
+      }
       res->cols.push_back(c);
     }
+    if (rowid_slot >= 0) {
+      DevColumn c;
+      c.dtype = DFGPU_UINT64;
+      c.values_bytes = size_t(n > 0 ? n : 1) * 8;
+      c.values = ctx->alloc(c.values_bytes);
+      scratch.cols.push_back(c);
+      kern_out[size_t(rowid_slot)] = c.values;
+    }
     if (n == 0) {
+      for (auto& c : res->cols)
+        if (c.dtype == DFGPU_UTF8) {
+          c.offsets = (int32_t*)ctx->alloc(4);
+          DF_CUDA(cudaMemsetAsync(c.offsets, 0, 4, ctx->stream));
+          c.values = ctx->alloc(1);
+        }
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
       res->nrows = 0;
       *out = res.release();
       return;
     }
     p.nrows = n;
     p.has_pred = has_pred;
-    p.nproj = nproj;
-    for (int i = 0; i < nproj; i++) p.out[i] = res->cols[size_t(i)].values;
+    p.nproj = nkern;
+    for (int i = 0; i < nkern; i++) p.out[i] = kern_out[size_t(i)];
     // tile_status is sized for the smallest tile either kernel uses (1024 rows)
     const size_t max_tiles = size_t((n + 1023) / 1024) + 1;
     unsigned long long* status = (unsigned long long*)ctx->alloc(max_tiles * 8);
@@ -306,7 +350,7 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       }
       if (ok) p.pred_fast = fp;
     }
-    for (int i = 0; i < nproj; i++) p.proj_fast[i] = fast_of(i + has_pred, false);
+    for (int i = 0; i < nkern; i++) p.proj_fast[i] = fast_of(i + has_pred, false);
     if (ctx->force_direct_kernel || !launch_fp_tma(ctx, p)) {
       p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
       const int d = p.ps.max_depth;
@@ -320,6 +364,11 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     ctx->free(status);
     if ((unsigned)ctx->h_scratch[2] != 0) fail(DFGPU_ERR_ARROW, "DivideByZero");
     res->nrows = has_pred ? (int64_t)ctx->h_scratch[0] : n;
+    for (int i = 0; i < nproj; i++)
+      if (out_kind[size_t(i)] < 0)
+        gather_utf8(ctx, batch->cols[size_t(-1 - out_kind[size_t(i)])], (const unsigned long long*)scratch.cols[0].values, res->nrows,
+                    &res->cols[size_t(i)]);
+    if (any_utf8) DF_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = res.release();
   });
 }

@@ -308,9 +308,10 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       src.stage = ringA + (size_t)s * p.stage_bytesA;
       src.col_off = p.col_offA;
       src.lrow0 = warp * 32 * K + lane;
+      src.row0 = (long long)tile * TILE + src.lrow0;
       src.valid = KMASK;
       if (tile == p.ntiles - 1) {  // only the last tile can be ragged
-        const long long row0 = (long long)tile * TILE + src.lrow0;
+        const long long row0 = src.row0;
         src.valid = 0;
 #pragma unroll
         for (int k = 0; k < K; k++)
@@ -364,6 +365,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       }
       src.col_off = p.col_offB;
       src.lrow0 = warp * 32 * K + lane;
+      src.row0 = (long long)tile * TILE + src.lrow0;
       src.valid = flags;  // a zero divisor only matters on rows that survive the filter
       for (int q = 0; q < p.nproj; q++) {
         const int prog = q + p.has_pred;

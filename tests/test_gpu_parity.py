@@ -75,6 +75,33 @@ def test_golden_csv_query_with_predicate(ctx, golden, fmt_f64):
     assert got == [l.split("\t", 1)[1] for l in exp_lines]
 
 
+def test_golden_csv_query_with_predicate_full(ctx, golden, fmt_f64):
+    # tests/sql.rs:30-37 including the Utf8 column (GPU Utf8 gather, filter.rs:93-103)
+    c = golden["uk_cities"]
+    arrays = [c["city"], np.array(c["lat"]), np.array(c["lng"])]
+    pred = (col(1) > lit(51.0)) & (col(1) < lit(53).cast(A.FLOAT64))
+    out = gpu_fp(ctx, arrays, pred, [col(0), col(1), col(2), col(1) + col(2)])
+    s = "".join('"%s"\t%s\t%s\t%s\n' % (a, fmt_f64(b), fmt_f64(c_), fmt_f64(d)) for a, b, c_, d in zip(*out))
+    assert s == golden["csv_query_with_predicate"]["expected"]
+
+
+def test_utf8_gather_vs_oracle(ctx):
+    rng = np.random.default_rng(17)
+    n = 200_000
+    words = ["", "a", "bc", "déjà vu", "x" * 40, "London, UK", "\"quoted\""]
+    strs = [words[i] + str(i % 977) * (i % 3) for i in rng.integers(0, len(words), n)]
+    v = rng.random(n)
+    for pred in [col(1) > lit(0.5), col(1) > lit(0.999), col(1) > lit(-1.0), col(1) > lit(2.0), None]:
+        got = gpu_fp(ctx, [strs, v], pred, [col(0), col(1) * col(1), col(0)])
+        exp = O.filter_project([strs, v], pred, [col(0), col(1) * col(1), col(0)])
+        assert got[0] == exp[0] and got[2] == exp[2]
+        assert np.array_equal(got[1], exp[1])
+    # FilterRelation alone: every input column, Utf8 included (filter.rs:55-57)
+    got = gpu_fp(ctx, [strs, v], col(1) < lit(0.25), [])
+    exp = O.filter_project([strs, v], col(1) < lit(0.25), [])
+    assert got[0] == exp[0] and np.array_equal(got[1], exp[1])
+
+
 def test_golden_cast(ctx, golden):
     c = golden["uk_cities"]
     out = gpu_fp(ctx, [np.array(c["lat"])], None, [col(0).cast(A.INT32)])

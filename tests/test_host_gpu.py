@@ -42,6 +42,14 @@ def test_csv_query_with_predicate_numeric_columns(ctx, golden, fmt_f64):
     assert rel.next() is None
 
 
+def test_csv_query_with_predicate_verbatim(ctx, golden, fmt_f64):
+    # tests/sql.rs:30-37 exactly as the reference runs it: SQL text in, golden string out
+    register_cities(ctx)
+    rel = ctx.sql(golden["csv_query_with_predicate"]["sql"])
+    s = "".join('"%s"\t%s\t%s\t%s\n' % (a, fmt_f64(b), fmt_f64(c), fmt_f64(d)) for a, b, c, d in result_rows(rel))
+    assert s == golden["csv_query_with_predicate"]["expected"]
+
+
 def test_csv_query_cast(ctx, golden):
     register_cities(ctx)
     rows = result_rows(ctx.sql(golden["csv_query_cast"]["sql"]))
