@@ -169,7 +169,9 @@ __device__ __forceinline__ unsigned cmp_term(const FastOp& t, const unsigned cha
   return flags;
 }
 
-template <int DEPTH, int K, bool F64ONLY>
+// FAST: every program of the query is a fast shape, so the interpreter is not even compiled into
+// this instantiation (fewer registers, smaller code).
+template <int DEPTH, int K, bool F64ONLY, bool FAST>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TILE = TM_CWARPS * 32 * K;
@@ -318,14 +320,14 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           if (row0 + k * 32 < p.nrows) src.valid |= 1u << k;
       }
       unsigned flags;
-      if (p.pred_fast.nterms > 0) {
+      if (FAST || p.pred_fast.nterms > 0) {
         // fast shape: Float64 comparisons straight from the staged tile, joined by AND / OR
         flags = cmp_term<K>(p.pred_fast.term[0], src.stage, p.col_offA, src.lrow0);
         for (int t = 1; t < p.pred_fast.nterms; t++) {
           const unsigned ft = cmp_term<K>(p.pred_fast.term[t], src.stage, p.col_offA, src.lrow0);
           flags = p.pred_fast.conn[t] ? (flags | ft) : (flags & ft);
         }
-      } else {
+      } else if constexpr (!FAST) {
         unsigned long long v[K];
         const unsigned b = eval_program<DEPTH, K, F64ONLY>(p.ps, 0, src, v);
         bad = bad || (b != 0);
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         const int prog = q + p.has_pred;
         unsigned long long v[K];
         const FastOp& fo = p.proj_fast[q];
-        if (fo.kind == 1) {
+        if (fo.kind == 1 || (FAST && fo.kind < 2)) {
           const unsigned long long* A = (const unsigned long long*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
 #pragma unroll
           for (int k = 0; k < K; k++) v[k] = A[k * 32];
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
               }
               break;
           }
-        } else {
+        } else if constexpr (!FAST) {
           const unsigned b = eval_program<DEPTH, K, F64ONLY>(p.ps, prog, src, v);
           bad = bad || (b != 0);
         }
@@ -419,7 +421,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           const unsigned m = __ballot_sync(0xffffffffu, f);
           if (f) {
             const unsigned idx = run + __popc(m & lt_mask);
-            if (wide) ((unsigned long long*)o)[idx] = v[k];
+            if (FAST || wide) ((unsigned long long*)o)[idx] = v[k];
             else store_elem(o, odt, (long long)idx, v[k]);
           }
           run += __popc(m);
@@ -471,9 +473,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
   }
 }
 
-template <int DEPTH, int K, bool F64ONLY>
+template <int DEPTH, int K, bool F64ONLY, bool FAST>
 static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
-  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY>;
+  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 16384 + TM_HDR_BYTES));
@@ -491,8 +493,11 @@ static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
 
 template <int DEPTH, int K>
 static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
-  if (p.ps.f64_only) launch_one<DEPTH, K, true>(ctx, p, smem);
-  else launch_one<DEPTH, K, false>(ctx, p, smem);
+  bool fast = !p.has_pred || p.pred_fast.nterms > 0;
+  for (int q = 0; q < p.nproj; q++) fast = fast && p.proj_fast[q].kind > 0;
+  if (fast) launch_one<1, K, true, true>(ctx, p, smem);
+  else if (p.ps.f64_only) launch_one<DEPTH, K, true, false>(ctx, p, smem);
+  else launch_one<DEPTH, K, false, false>(ctx, p, smem);
 }
 
 bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
