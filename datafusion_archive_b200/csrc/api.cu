@@ -124,9 +124,32 @@ dfgpu_batch::~dfgpu_batch() {
     ctx->free(c.offsets);
   }
 }
+void* dfgpu_ctx::host_alloc(size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  HostBlock* best = nullptr;
+  for (auto& b : host_blocks)
+    if (!b.used && b.bytes >= bytes && b.bytes <= 2 * bytes + (1 << 20) && (!best || b.bytes < best->bytes)) best = &b;
+  if (best) {
+    best->used = true;
+    return best->p;
+  }
+  void* p = nullptr;
+  DF_CUDA(cudaMallocHost(&p, bytes));
+  host_blocks.push_back(HostBlock{p, bytes, true});
+  return p;
+}
+void dfgpu_ctx::host_release(void* p) {
+  for (auto& b : host_blocks)
+    if (b.p == p) b.used = false;
+}
+
 dfgpu_result::~dfgpu_result() {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (on_host) {
+    for (auto& c : cols) ctx->host_release(c.values);
+    return;
+  }
   for (auto& c : cols) {
     ctx->free(c.values);
     ctx->free(c.validity);
@@ -170,6 +193,8 @@ extern "C" int dfgpu_init(int device, dfgpu_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("DFGPU_FP_KERNEL")) ctx->force_direct_kernel = std::string(e) == "direct";
     DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream_in, cudaStreamNonBlocking));
+    DF_CUDA(cudaStreamCreateWithFlags(&ctx->stream_out, cudaStreamNonBlocking));
     DF_CUDA(cudaEventCreate(&ctx->ev_start));
     DF_CUDA(cudaEventCreate(&ctx->ev_stop));
     // keep freed blocks cached in the stream-ordered pool
@@ -200,6 +225,9 @@ extern "C" int dfgpu_shutdown(dfgpu_ctx* ctx) {
     for (int i = 0; i < dfgpu_ctx::kProfRing; i++)
       for (int j = 0; j < 2; j++)
         if (ctx->prof_ev[i][j]) cudaEventDestroy(ctx->prof_ev[i][j]);
+    for (auto& b : ctx->host_blocks) cudaFreeHost(b.p);
+    cudaStreamDestroy(ctx->stream_in);
+    cudaStreamDestroy(ctx->stream_out);
     cudaFree(ctx->d_scratch);
     cudaFreeHost(ctx->h_scratch);
     cudaEventDestroy(ctx->ev_start);
@@ -421,6 +449,11 @@ extern "C" int dfgpu_result_copy_col(const dfgpu_result* r, int i, void* dst_val
     const DevColumn& c = r->cols[size_t(i)];
     const int w = dtype_width(c.dtype);
     const size_t nb = w ? size_t(r->nrows) * size_t(w) : c.values_bytes;
+    if (r->on_host) {
+      if (nb && dst_values) memcpy(dst_values, c.values, nb);
+      if (dst_validity) memset(dst_validity, 0xff, size_t(r->nrows + 7) / 8);
+      return;
+    }
     if (nb && dst_values) DF_CUDA(cudaMemcpyAsync(dst_values, c.values, nb, cudaMemcpyDeviceToHost, ctx->stream));
     if (dst_validity) {
       const size_t vb = size_t(r->nrows + 7) / 8;
@@ -435,7 +468,15 @@ extern "C" int dfgpu_result_copy_col(const dfgpu_result* r, int i, void* dst_val
 extern "C" int dfgpu_result_col_device_ptr(const dfgpu_result* r, int i, const void** dptr) {
   return guarded([&] {
     if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    if (r->on_host) fail(DFGPU_ERR_GENERAL, "result lives in host memory: use dfgpu_result_col_host_ptr");
     *dptr = r->cols[size_t(i)].values;
+  });
+}
+extern "C" int dfgpu_result_col_host_ptr(const dfgpu_result* r, int i, const void** hptr) {
+  return guarded([&] {
+    if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");
+    if (!r->on_host) fail(DFGPU_ERR_GENERAL, "result lives in device memory: use dfgpu_result_copy_col");
+    *hptr = r->cols[size_t(i)].values;
   });
 }
 extern "C" int dfgpu_result_free(dfgpu_result* r) {

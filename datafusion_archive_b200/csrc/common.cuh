@@ -86,6 +86,12 @@ struct dfgpu_ctx {
   int prof_begin();          // returns ring slot or -1
   void prof_end(int slot);
   void prof_drain();
+  // streamed host->host operators: copy-in / copy-out streams and a cache of pinned result buffers
+  cudaStream_t stream_in = nullptr, stream_out = nullptr;
+  struct HostBlock { void* p; size_t bytes; bool used; };
+  std::vector<HostBlock> host_blocks;
+  void* host_alloc(size_t bytes);   // pinned, cached
+  void host_release(void* p);
   // multi-GPU
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
@@ -115,5 +121,6 @@ struct dfgpu_result {
   dfgpu_ctx* ctx = nullptr;
   int64_t nrows = 0;
   std::vector<DevColumn> cols;
+  bool on_host = false;  // columns live in pinned host memory (dfgpu_filter_project_host)
   ~dfgpu_result();
 };

@@ -372,3 +372,160 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     *out = res.release();
   });
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host -> host, chunk-pipelined (see include/dfgpu.h).  All H2D copies are queued up front on the
+// copy-in stream; chunk c's kernel waits for its copies only; its compacted output is copied back
+// on the copy-out stream while chunk c+1 is being filtered and chunk c+2 uploaded.
+// ---------------------------------------------------------------------------------------------
+extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, const dfgpu_insn* pred, int pred_len,
+                                         const dfgpu_insn* const* proj, const int* proj_len, int nproj, int64_t chunk_rows,
+                                         dfgpu_result** out) {
+  return guarded([&] {
+    if (!ctx || !out || !cols || ncols < 1) fail(DFGPU_ERR_GENERAL, "dfgpu_filter_project_host: null argument");
+    ctx->use();
+    const long long n = cols[0].len;
+    for (int i = 0; i < ncols; i++) {
+      if (cols[i].len != n) fail(DFGPU_ERR_GENERAL, "all columns of a RecordBatch must have the same length");
+    }
+    // nproj == 0 -> every input column
+    std::vector<dfgpu_insn> ident;
+    std::vector<const dfgpu_insn*> pptr;
+    std::vector<int> plen;
+    if (nproj == 0) {
+      ident.resize(size_t(ncols));
+      for (int i = 0; i < ncols; i++) {
+        memset(&ident[size_t(i)], 0, sizeof(dfgpu_insn));
+        ident[size_t(i)].op = DFGPU_OP_COL;
+        ident[size_t(i)].col = i;
+        ident[size_t(i)].dtype = cols[i].dtype;
+        pptr.push_back(&ident[size_t(i)]);
+        plen.push_back(1);
+      }
+      nproj = ncols;
+      proj = pptr.data();
+      proj_len = plen.data();
+    }
+    // referenced columns only (the reference uploads nothing, but gathers every column: filter.rs:55-57)
+    std::vector<int> remap(size_t(ncols), -1), used;
+    auto scan = [&](const dfgpu_insn* p, int len) {
+      for (int i = 0; i < len; i++)
+        if (p[i].op == DFGPU_OP_COL) {
+          if (p[i].col < 0 || p[i].col >= ncols) fail(DFGPU_ERR_INVALID_COLUMN, "column index " + std::to_string(p[i].col) + " out of range");
+          if (remap[size_t(p[i].col)] < 0) {
+            remap[size_t(p[i].col)] = int(used.size());
+            used.push_back(p[i].col);
+          }
+        }
+    };
+    if (pred_len > 0) scan(pred, pred_len);
+    for (int q = 0; q < nproj; q++) scan(proj[q], proj_len[q]);
+    if (used.empty()) fail(DFGPU_ERR_NOT_IMPLEMENTED, "queries that reference no column");
+    for (int c : used) {
+      if (!is_numeric(cols[c].dtype)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "dfgpu_filter_project_host handles fixed-width numeric columns only");
+      if (cols[c].validity) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
+    }
+    auto rewrite = [&](const dfgpu_insn* p, int len) {
+      std::vector<dfgpu_insn> v(p, p + len);
+      for (auto& in : v)
+        if (in.op == DFGPU_OP_COL) in.col = remap[size_t(in.col)];
+      return v;
+    };
+    std::vector<dfgpu_insn> pred2 = pred_len > 0 ? rewrite(pred, pred_len) : std::vector<dfgpu_insn>();
+    std::vector<std::vector<dfgpu_insn>> proj2;
+    std::vector<const dfgpu_insn*> proj2p;
+    std::vector<int> proj2l;
+    for (int q = 0; q < nproj; q++) {
+      proj2.push_back(rewrite(proj[q], proj_len[q]));
+    }
+    for (auto& v : proj2) {
+      proj2p.push_back(v.data());
+      proj2l.push_back(int(v.size()));
+    }
+
+    if (chunk_rows <= 0) chunk_rows = 8ll << 20;
+    const long long nchunks = n > 0 ? (n + chunk_rows - 1) / chunk_rows : 1;
+    struct Chunk {
+      dfgpu_batch batch;
+      dfgpu_result* res = nullptr;
+      cudaEvent_t ev = nullptr;
+    };
+    std::vector<std::unique_ptr<Chunk>> chunks;
+    struct Cleanup {
+      std::vector<std::unique_ptr<Chunk>>* c;
+      dfgpu_ctx* ctx;
+      ~Cleanup() {
+        cudaStreamSynchronize(ctx->stream_in);
+        cudaStreamSynchronize(ctx->stream_out);
+        for (auto& ch : *c) {
+          if (ch->res) delete ch->res;
+          if (ch->ev) cudaEventDestroy(ch->ev);
+        }
+      }
+    } cleanup{&chunks, ctx};
+    // make the allocations (ordered on ctx->stream) visible to the copy-in stream
+    cudaEvent_t ev_alloc;
+    DF_CUDA(cudaEventCreateWithFlags(&ev_alloc, cudaEventDisableTiming));
+    for (long long c = 0; c < nchunks; c++) {
+      auto ch = std::make_unique<Chunk>();
+      ch->batch.ctx = ctx;
+      const long long r0 = c * (long long)chunk_rows, rows = std::min<long long>((long long)chunk_rows, n - r0);
+      ch->batch.nrows = rows > 0 ? rows : 0;
+      for (int u : used) {
+        DevColumn d;
+        d.dtype = cols[u].dtype;
+        d.values_bytes = size_t(ch->batch.nrows) * size_t(dtype_width(d.dtype));
+        d.values = ctx->alloc(d.values_bytes);
+        ch->batch.cols.push_back(d);
+      }
+      DF_CUDA(cudaEventCreateWithFlags(&ch->ev, cudaEventDisableTiming));
+      chunks.push_back(std::move(ch));
+    }
+    DF_CUDA(cudaEventRecord(ev_alloc, ctx->stream));
+    DF_CUDA(cudaStreamWaitEvent(ctx->stream_in, ev_alloc, 0));
+    cudaEventDestroy(ev_alloc);
+    for (long long c = 0; c < nchunks; c++) {
+      Chunk& ch = *chunks[size_t(c)];
+      const long long r0 = c * chunk_rows;
+      for (size_t k = 0; k < used.size(); k++) {
+        const dfgpu_col& hc = cols[used[k]];
+        const int w = dtype_width(hc.dtype);
+        if (ch.batch.nrows > 0)
+          DF_CUDA(cudaMemcpyAsync(ch.batch.cols[k].values, static_cast<const uint8_t*>(hc.values) + size_t(hc.offset + r0) * size_t(w),
+                                  size_t(ch.batch.nrows) * size_t(w), cudaMemcpyHostToDevice, ctx->stream_in));
+      }
+      DF_CUDA(cudaEventRecord(ch.ev, ctx->stream_in));
+    }
+    // filter chunk by chunk; outputs go back as soon as their size is known
+    auto res = std::make_unique<dfgpu_result>();
+    res->ctx = ctx;
+    res->on_host = true;
+    long long off = 0;
+    for (long long c = 0; c < nchunks; c++) {
+      Chunk& ch = *chunks[size_t(c)];
+      DF_CUDA(cudaStreamWaitEvent(ctx->stream, ch.ev, 0));
+      int rc = dfgpu_filter_project(ctx, &ch.batch, pred2.data(), int(pred2.size()), proj2p.data(), proj2l.data(), nproj, &ch.res);
+      if (rc != 0) fail(rc, dfgpu_last_error());
+      if (c == 0) {
+        for (int q = 0; q < nproj; q++) {
+          DevColumn hcol;
+          hcol.dtype = ch.res->cols[size_t(q)].dtype;
+          hcol.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(hcol.dtype));
+          hcol.values = ctx->host_alloc(hcol.values_bytes);
+          res->cols.push_back(hcol);
+        }
+      }
+      // the kernel of this chunk has completed (dfgpu_filter_project synchronised ctx->stream)
+      for (int q = 0; q < nproj; q++) {
+        const int w = dtype_width(res->cols[size_t(q)].dtype);
+        if (ch.res->nrows > 0)
+          DF_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(res->cols[size_t(q)].values) + size_t(off) * size_t(w), ch.res->cols[size_t(q)].values,
+                                  size_t(ch.res->nrows) * size_t(w), cudaMemcpyDeviceToHost, ctx->stream_out));
+      }
+      off += ch.res->nrows;
+    }
+    DF_CUDA(cudaStreamSynchronize(ctx->stream_out));
+    res->nrows = off;
+    *out = res.release();
+  });
+}

@@ -66,6 +66,8 @@ def lib():
     L.dfgpu_batch_rows.argtypes = [vp, C.POINTER(C.c_int64)]
     L.dfgpu_batch_free.argtypes = [vp]
     L.dfgpu_filter_project.argtypes = [vp, vp, PI, C.c_int, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.dfgpu_filter_project_host.argtypes = [vp, C.POINTER(A.Col), C.c_int, PI, C.c_int, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.c_int64, C.POINTER(vp)]
+    L.dfgpu_result_col_host_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.dfgpu_aggregate_create.argtypes = [vp, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(A.Agg), C.c_int, C.c_int64, C.POINTER(vp)]
     L.dfgpu_aggregate_update.argtypes = [vp, vp]
     L.dfgpu_aggregate_finish.argtypes = [vp, C.POINTER(vp)]
@@ -120,6 +122,14 @@ class Result:
         dt = C.c_int32()
         check(lib().dfgpu_result_col_dtype(self.h, i, C.byref(dt)))
         return dt.value
+
+    def host_view(self, i):
+        """Zero-copy numpy view of column i of a host-resident result (filter_project_host)."""
+        p = C.c_void_p()
+        check(lib().dfgpu_result_col_host_ptr(self.h, i, C.byref(p)))
+        dt = np.dtype(A.NP_OF[self.dtype(i)])
+        buf = (C.c_uint8 * (self.nrows * dt.itemsize)).from_address(p.value) if self.nrows else (C.c_uint8 * 0)()
+        return np.frombuffer(buf, dtype=dt, count=self.nrows)
 
     def copy_into(self, i, dst):
         """Copy column i into a caller-allocated numpy buffer (first nrows elements)."""
@@ -218,6 +228,18 @@ class GpuContext:
         ptrs, lens, n = A.make_programs([e.program(schema) for e in proj], keep)
         out = C.c_void_p()
         check(lib().dfgpu_filter_project(self.h, batch.h, parr, len(pprog), ptrs, lens, n, C.byref(out)))
+        return Result(self, out)
+
+    def filter_project_host(self, arrays, pred=None, proj=(), chunk_rows=0):
+        """Host buffers in, host (pinned) buffers out; upload / kernel / download pipelined by chunk."""
+        keep = []
+        cols = A.make_cols(arrays, keep)
+        schema = [cols[i].dtype for i in range(len(arrays))]
+        pprog = pred.program(schema) if pred is not None else []
+        parr = (A.Insn * max(1, len(pprog)))(*pprog)
+        ptrs, lens, n = A.make_programs([e.program(schema) for e in proj], keep)
+        out = C.c_void_p()
+        check(lib().dfgpu_filter_project_host(self.h, cols, len(arrays), parr, len(pprog), ptrs, lens, n, chunk_rows, C.byref(out)))
         return Result(self, out)
 
     # -- AggregateRelation ------------------------------------------------------------------------

@@ -173,6 +173,16 @@ int dfgpu_batch_free(dfgpu_batch* b);
 int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_insn* pred, int pred_len,
                          const dfgpu_insn* const* proj, const int* proj_len, int nproj, dfgpu_result** out);
 
+/* Same operator, host buffers in, host buffers out, for one big RecordBatch: the batch is cut into
+ * row-range chunks and upload (H2D), kernel and download (D2H) of successive chunks overlap on three
+ * streams; only the referenced columns cross PCIe.  This is what GpuFilterProjectRelation::next calls
+ * for large batches.  The result's columns live in pinned host memory owned by the library
+ * (dfgpu_result_col_host_ptr for zero-copy, dfgpu_result_copy_col to copy out); numeric outputs only.
+ * Input buffers should be pinned (dfgpu_host_alloc) for the copies to be asynchronous. */
+int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, const dfgpu_insn* pred, int pred_len,
+                              const dfgpu_insn* const* proj, const int* proj_len, int nproj, int64_t chunk_rows /*0 = default*/,
+                              dfgpu_result** out);
+
 /* ---- AggregateRelation (src/execution/aggregate.rs:38-61, 615-631, 703-952) ----
  * create → update once per input batch (the `while let Some(batch)` loops at aggregate.rs:707,796)
  * → finish (materialise group columns then aggregate columns: aggregate.rs:890-949; with a
@@ -196,6 +206,8 @@ int dfgpu_result_col_nulls(const dfgpu_result* r, int i, int64_t* null_count);
 /* Copy column i to host.  dst_values: nrows*width bytes (Utf8: nbytes); dst_validity: ceil(nrows/8)
  * bytes or NULL; dst_offsets: (nrows+1) i32 for Utf8, else NULL. */
 int dfgpu_result_copy_col(const dfgpu_result* r, int i, void* dst_values, uint8_t* dst_validity, int32_t* dst_offsets);
+/* Host pointer of column i's values (results of dfgpu_filter_project_host only). */
+int dfgpu_result_col_host_ptr(const dfgpu_result* r, int i, const void** hptr);
 /* Device pointer of column i's values (for zero-copy consumers on the same GPU). */
 int dfgpu_result_col_device_ptr(const dfgpu_result* r, int i, const void** dptr);
 int dfgpu_result_free(dfgpu_result* r);

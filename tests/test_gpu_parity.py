@@ -158,6 +158,31 @@ def test_c3_fused_expr_filter(ctx):
     assert np.array_equal(got[0], (a + b)[m]) and np.array_equal(got[1], (a * b)[m])
 
 
+def test_host_pipelined_matches_resident_path(ctx):
+    # dfgpu_filter_project_host: chunked upload / kernel / download; same rows, same order, same bits
+    arrays, pred, proj = workloads.c3(3_000_017)
+    exp = O.filter_project(arrays, pred, proj)
+    for chunk in [0, 1 << 20, 999_983, 4_000_000]:
+        r = ctx.filter_project_host(arrays, pred, proj, chunk_rows=chunk)
+        got = [r.host_view(i).copy() for i in range(r.ncols)]
+        r.free()
+        assert_cols_bit_equal(got, exp)
+    # pinned inputs, unreferenced Utf8 column present, no predicate, empty input
+    pin = engine.PinnedBuffer((1_000_000,), np.float64)
+    pin.array[:] = np.random.default_rng(2).random(1_000_000)
+    strs = ["x"] * 1_000_000
+    r = ctx.filter_project_host([strs, pin.array], None, [col(1) * lit(2.0)], chunk_rows=300_000)
+    assert np.array_equal(r.host_view(0), pin.array * 2.0)
+    r.free()
+    r = ctx.filter_project_host([np.array([], dtype=np.float64)], col(0) > lit(0.5), [col(0)])
+    assert r.nrows == 0
+    r.free()
+    with pytest.raises(engine.DfGpuError) as e:
+        ctx.filter_project_host([pin.array], None, [col(0) / lit(0.0)])
+    assert e.value.code == A.ERR_ARROW
+    pin.free()
+
+
 def test_filter_emits_all_columns_when_no_projection(ctx):
     # FilterRelation alone gathers every input column (filter.rs:55-57)
     arrays, pred, _ = workloads.c3(50_000)
@@ -299,6 +324,48 @@ def test_groupby_table_growth_all_distinct_keys(ctx):
     assert np.array_equal(got[0], k[order])
     assert np.array_equal(got[1], v[order]) and np.array_equal(got[3], v[order])
     assert np.all(got[2] == 1)
+
+
+def test_groupby_low_cardinality_front_table(ctx):
+    # few groups in a big batch: the sampled prefix routes the bulk through the shared-memory front table
+    n = 6_000_000
+    rng = np.random.default_rng(31)
+    for ngroups in [1, 7, 900]:
+        k = workloads.mix_keys(rng.integers(0, ngroups, n, dtype=np.int64))
+        k[::1000] = -1  # the key that equals the empty marker takes the global path
+        v = rng.random(n)
+        iv = rng.integers(-50, 50, n, dtype=np.int64)
+        aggs = [AggregateFunction("sum", col(1)), AggregateFunction("count", col(1)), AggregateFunction("min", col(1)),
+                AggregateFunction("max", col(1)), AggregateFunction("sum", col(2))]
+        got = sort_by_key(gpu_agg(ctx, [k, v, iv], [col(0)], aggs))
+        uk, inv = np.unique(k, return_inverse=True)
+        assert np.array_equal(got[0], uk)
+        np.testing.assert_allclose(got[1], np.bincount(inv, weights=v), rtol=SUM_RTOL)
+        assert np.array_equal(got[2], np.bincount(inv).astype(np.uint64))
+        mn = np.full(len(uk), np.inf); np.minimum.at(mn, inv, v)
+        mx = np.full(len(uk), -np.inf); np.maximum.at(mx, inv, v)
+        assert np.array_equal(got[3], mn) and np.array_equal(got[4], mx)
+        assert np.array_equal(got[5], np.bincount(inv, weights=iv).astype(np.int64))
+
+
+def test_groupby_high_cardinality_layouts(ctx):
+    # (a) cardinality hint -> AoS table from the start; (b) no hint: the sampled prefix switches layouts
+    n = 5_000_000
+    rng = np.random.default_rng(33)
+    k = workloads.mix_keys(rng.integers(0, 1_500_000, n, dtype=np.int64))
+    v = rng.random(n)
+    aggs = [AggregateFunction("min", col(1)), AggregateFunction("max", col(1)), AggregateFunction("sum", col(1)), AggregateFunction("count", col(1))]
+    uk, inv = np.unique(k, return_inverse=True)
+    mn = np.full(len(uk), np.inf); np.minimum.at(mn, inv, v)
+    mx = np.full(len(uk), -np.inf); np.maximum.at(mx, inv, v)
+    for hint in [2_000_000, 0]:
+        got = sort_by_key(gpu_agg(ctx, [k, v], [col(0)], aggs, expected=hint))
+        assert np.array_equal(got[0], uk) and np.array_equal(got[1], mn) and np.array_equal(got[2], mx)
+        np.testing.assert_allclose(got[3], np.bincount(inv, weights=v), rtol=SUM_RTOL)
+        assert np.array_equal(got[4], np.bincount(inv).astype(np.uint64))
+    # two batches: the second one finds the table already converted
+    got = sort_by_key(gpu_agg(ctx, [k, v], [col(0)], aggs, nbatches=2))
+    assert np.array_equal(got[0], uk) and np.array_equal(got[4], np.bincount(inv).astype(np.uint64))
 
 
 def test_groupby_sentinel_and_extreme_keys(ctx):
