@@ -39,6 +39,14 @@ sys.path.insert(0, ROOT)
 METRIC = "rows/s filter+agg over 1e8-row Arrow batch (C2: SELECT a FROM t WHERE a>0.5, Float64)"
 
 
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu capture (profiles/)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key)
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -213,7 +221,7 @@ def run_ours(args):
                 "path": "dfgpu_filter_project_host: pinned host batch -> chunked H2D | kernel | D2H pipeline -> pinned host result"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_filter_project", "kernel_ms": kernel_ms,
+                     "traffic": ncu_traffic("k_filter_project:c2") if n == 100_000_000 else None, "kernel": "k_filter_project_tma", "kernel_ms": kernel_ms,
                      "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
     }
 

@@ -211,7 +211,10 @@ constexpr int AG_FRONT_MAX_GROUPS = 1024;
 // and is merged into the global table once, when the CTA is done.  Used when the sampled prefix shows
 // few groups: with a handful of hot keys every global reduction would serialise on the same L2 sector
 // (measured: 10 groups, 1e8 rows: 21 ms through L2 atomics).
-template <int DEPTH, bool FRONT>
+// NULLS: like the reference, keys and MIN/MAX/SUM arguments are read ignoring the validity bitmap
+// (`array.value(row)`, aggregate.rs:561-601, 807-852; a null produced by arithmetic reads as the
+// builder's default 0); only COUNT (an extension, §DESIGN) honours nulls.
+template <int DEPTH, bool FRONT, bool NULLS>
 __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__ AggParams p) {
   extern __shared__ unsigned long long s_front[];  // FRONT: keys[AG_FRONT_SLOTS] then vals[naggs][AG_FRONT_SLOTS]
   __shared__ int s_full;
@@ -245,7 +248,8 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     for (int r = 0; r < AG_R; r++) key[r] = 0;
     for (int k = 0; k < p.nkeys; k++) {
       unsigned long long v[AG_R];
-      const unsigned b = eval_program<DEPTH, AG_R, false>(p.ps, k, src, v);
+      unsigned kv;
+      const unsigned b = eval_program_n<DEPTH, AG_R, false, NULLS>(p.ps, k, src, v, kv);
       bad = bad || (b != 0);
 #pragma unroll
       for (int r = 0; r < AG_R; r++) key[r] |= (v[r] & p.key_mask[k]) << p.key_shift[k];
@@ -291,12 +295,14 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     // accumulators (update_accumulators, aggregate.rs:548-612): argument evaluated once per row
     for (int g = 0; g < p.nargs; g++) {
       unsigned long long v[AG_R];
-      const unsigned b = eval_program<DEPTH, AG_R, false>(p.ps, p.nkeys + g, src, v);
+      unsigned av;
+      const unsigned b = eval_program_n<DEPTH, AG_R, false, NULLS>(p.ps, p.nkeys + g, src, v, av);
       for (int a = 0; a < p.naggs; a++) {
         if (p.agg_arg[a] != g) continue;
         const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
 #pragma unroll
         for (int r = 0; r < AG_R; r++) {
+          if (NULLS && func == DFGPU_AGG_COUNT && !((av >> r) & 1u)) continue;  // COUNT counts non-null values
           if (FRONT && fslot[r] >= 0) {
             acc_fold_shared(func, mt, &s_front[(1 + a) * AG_FRONT_SLOTS + fslot[r]], v[r]);
             if ((b >> r) & 1u) bad = true;
@@ -337,10 +343,16 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
 constexpr int RD_R = 8;  // rows per thread per tile in the column reduce (more bytes in flight per SM)
 constexpr int RD_TILE = AG_THREADS * RD_R;
 
-template <int DEPTH>
+// NULLS: array_ops::{min,max,sum} skip nulls and report None when nothing was non-null
+// (restated from arrow 0.12; call sites aggregate.rs:347-541): the number of non-null inputs per
+// aggregate is accumulated in counters[8 + a] so finish can emit a null.
+template <int DEPTH, bool NULLS>
 __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ AggParams p) {
   __shared__ unsigned long long s_acc[kMaxAggs][AG_THREADS];
   __shared__ unsigned long long s_red[AG_THREADS / 32];
+  unsigned nn[kMaxAggs];
+#pragma unroll
+  for (int a = 0; a < kMaxAggs; a++) nn[a] = 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int a = 0; a < p.naggs; a++) s_acc[a][tid] = agg_identity(p.aggs[a].func);
   bool bad = false;
@@ -356,16 +368,19 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
     }
     for (int g = 0; g < p.nargs; g++) {
       unsigned long long v[RD_R];
-      const unsigned b = eval_program<DEPTH, RD_R, false>(p.ps, g, src, v);
+      unsigned av;
+      const unsigned b = eval_program_n<DEPTH, RD_R, false, NULLS>(p.ps, g, src, v, av);
       bad = bad || (b != 0);
-      for (int a = 0; a < p.naggs; a++) {
-        if (p.agg_arg[a] != g) continue;
+#pragma unroll
+      for (int a = 0; a < kMaxAggs; a++) {
+        if (a >= p.naggs || p.agg_arg[a] != g) continue;
         const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
         unsigned long long acc = s_acc[a][tid];
 #pragma unroll
         for (int r = 0; r < RD_R; r++)
-          if (rows[r] >= 0) acc = acc_fold(func, mt, acc, v[r]);
+          if (rows[r] >= 0 && (!NULLS || ((av >> r) & 1u))) acc = acc_fold(func, mt, acc, v[r]);
         s_acc[a][tid] = acc;
+        if (NULLS) nn[a] += __popc(av & src.valid);
       }
     }
   }
@@ -383,6 +398,15 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
       if (lane == 0) acc_merge_global(func, mt, p.t.val(0, a), acc);  // cap == 0: slot 0
     }
     __syncthreads();
+  }
+  if (NULLS) {
+#pragma unroll
+    for (int a = 0; a < kMaxAggs; a++) {
+      unsigned c = nn[a];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0 && c && a < p.naggs) atomicAdd(&p.counters[8 + a], (unsigned long long)c);
+    }
   }
   if (bad) p.counters[3] = 1ull;
 }
@@ -515,6 +539,8 @@ struct dfgpu_aggstate {
   TableLayout t{nullptr, 0, 0, 0};
   bool aos = false;
   bool use_front = false;  // route rows through the per-CTA shared-memory front table
+  bool saw_nulls = false;  // some batch went through the null-aware reduce: per-aggregate non-null counts are on the device
+  std::vector<long long> nonnull_host = std::vector<long long>(8, 0);
   unsigned long long* d_counters = nullptr;  // 8 x u64
   long long ngroups = 0;
   bool sentinel_used = false;
@@ -633,10 +659,10 @@ void table_grow(dfgpu_aggstate* st, long long new_cap) {
   st->cap = new_cap;
 }
 
-template <int DEPTH, bool FRONT>
+template <int DEPTH, bool FRONT, bool NULLS = false>
 void launch_hash_agg_f(dfgpu_ctx* ctx, const AggParams& p, long long n) {
   const size_t smem = FRONT ? size_t(AG_FRONT_SLOTS) * 8 * size_t(1 + p.naggs) : 0;
-  auto kern = k_hash_agg<DEPTH, FRONT>;
+  auto kern = k_hash_agg<DEPTH, FRONT, NULLS>;
   if (FRONT) {
     static bool configured = false;
     if (!configured) {
@@ -658,13 +684,13 @@ void launch_hash_agg(dfgpu_ctx* ctx, const AggParams& p, long long n, bool front
   if (front) launch_hash_agg_f<DEPTH, true>(ctx, p, n);
   else launch_hash_agg_f<DEPTH, false>(ctx, p, n);
 }
-template <int DEPTH>
+template <int DEPTH, bool NULLS = false>
 void launch_reduce(dfgpu_ctx* ctx, const AggParams& p, long long n) {
   int per_sm = 0;
-  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce<DEPTH>, AG_THREADS, 0));
+  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce<DEPTH, NULLS>, AG_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
   const int ps = ctx->prof_begin();
-  k_reduce<DEPTH><<<grid_for(ctx, n, RD_TILE, per_sm), AG_THREADS, 0, ctx->stream>>>(p);
+  k_reduce<DEPTH, NULLS><<<grid_for(ctx, n, RD_TILE, per_sm), AG_THREADS, 0, ctx->stream>>>(p);
   DF_CUDA(cudaGetLastError());
   ctx->prof_end(ps);
   ctx->launches++;
@@ -695,8 +721,8 @@ extern "C" int dfgpu_aggregate_create(dfgpu_ctx* ctx, const dfgpu_insn* const* k
       st->funcs.push_back(aggs[a].func);
       st->out_dtypes.push_back(aggs[a].out_dtype);
     }
-    st->d_counters = (unsigned long long*)ctx->alloc(64);
-    DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 64, ctx->stream));
+    st->d_counters = (unsigned long long*)ctx->alloc(128);  // [0..7] see AggParams, [8..15] non-null inputs per aggregate
+    DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 128, ctx->stream));
     *out = st.release();
   });
 }
@@ -707,8 +733,6 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     if (st->finished) fail(DFGPU_ERR_GENERAL, "aggregate already finished");
     dfgpu_ctx* ctx = st->ctx;
     ctx->use();
-    for (const auto& c : batch->cols)
-      if (c.null_count > 0) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
     if (batch->nrows >= (1ll << 32)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "batches of 2^32 rows or more");
 
     AggParams p;
@@ -801,10 +825,17 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     if (st->nkeys == 0) {
       p.t = st->t;
       p.cap = 0;
-      if (d <= 1) launch_reduce<1>(ctx, p, p.nrows);
-      else if (d <= 2) launch_reduce<2>(ctx, p, p.nrows);
-      else if (d <= 4) launch_reduce<4>(ctx, p, p.nrows);
-      else launch_reduce<8>(ctx, p, p.nrows);
+      if (p.ps.has_nulls) {
+        if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "nullable inputs with a multi-GPU communicator");
+        st->saw_nulls = true;
+        launch_reduce<8, true>(ctx, p, p.nrows);
+      } else {
+        for (int a = 0; a < st->naggs; a++) st->nonnull_host[size_t(a)] += batch->nrows;
+        if (d <= 1) launch_reduce<1>(ctx, p, p.nrows);
+        else if (d <= 2) launch_reduce<2>(ctx, p, p.nrows);
+        else if (d <= 4) launch_reduce<4>(ctx, p, p.nrows);
+        else launch_reduce<8>(ctx, p, p.nrows);
+      }
       unsigned long long c[4];
       read_counters(st, c);
       if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
@@ -847,7 +878,8 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         DF_CUDA(cudaMemsetAsync(st->d_counters + 1, 0, 8, ctx->stream));
         const long long n = list ? nlist : p.nrows;
         const bool front = st->use_front && !list;
-        if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
+        if (p.ps.has_nulls) launch_hash_agg_f<8, false, true>(ctx, p, n);
+        else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
         else if (d <= 4) launch_hash_agg<4>(ctx, p, n, front);
         else launch_hash_agg<8>(ctx, p, n, front);
@@ -1025,9 +1057,18 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
     res->nrows = cnt;
-    if (st->nkeys == 0 && st->rows_seen == 0) {
-      // no input rows: every aggregate is null (array_from_scalar!, aggregate.rs:641-643)
-      for (auto& c : res->cols) {
+    if (st->nkeys == 0) {
+      // an aggregate that saw no non-null input is null (array_from_scalar!, aggregate.rs:641-643)
+      std::vector<long long> nonnull = st->nonnull_host;
+      if (st->saw_nulls) {
+        DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 40, st->d_counters + 8, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        DF_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int a = 0; a < st->naggs; a++) nonnull[size_t(a)] += (long long)ctx->h_scratch[40 + a];
+      }
+      if (ctx->world > 1) for (int a = 0; a < st->naggs; a++) nonnull[size_t(a)] = st->rows_seen;  // rows_seen was all-reduced
+      for (int a = 0; a < st->naggs; a++) {
+        if (nonnull[size_t(a)] > 0 || (st->rows_seen > 0 && st->descs[size_t(a)].func == DFGPU_AGG_COUNT)) continue;
+        DevColumn& c = res->cols[size_t(a)];
         c.validity = (uint8_t*)ctx->alloc(1);
         DF_CUDA(cudaMemsetAsync(c.validity, 0, 1, ctx->stream));
         c.null_count = 1;

@@ -157,6 +157,25 @@ int ProgramBuilder::add(const dfgpu_insn* p, int n, const char* what) {
 
   // 2. tree -> bytecode with right-hand leaf folding; track the live register-stack depth
   CompiledProgram cp;
+  {
+    // can the result be null?  (columns with nulls propagate through arithmetic / And / Or / Cast;
+    // comparisons never produce nulls)
+    struct N {
+      const dfgpu_batch* b;
+      bool go(const Node* nd) const {
+        switch (nd->kind) {
+          case Node::COL: return b->cols[size_t(nd->col)].null_count > 0;
+          case Node::LIT: return false;
+          case Node::CAST: return go(nd->l.get());
+          default: {
+            const bool cmp = nd->op >= DFGPU_OP_EQ && nd->op <= DFGPU_OP_GE;
+            return !cmp && (go(nd->l.get()) || go(nd->r.get()));
+          }
+        }
+      }
+    } nn{batch_};
+    cp.nullable = nn.go(st[0].get());
+  }
   int depth = 0;
   struct Emit {
     ProgramBuilder* pb;
@@ -250,6 +269,7 @@ void ProgramBuilder::finish(ProgramSet* out) const {
       fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression programs exceed " + std::to_string(kMaxInsn) + " instructions");
     for (const auto& di : progs_[i].code) out->insn[pc++] = di;
     out->out_dtype[i] = uint8_t(progs_[i].out_dtype);
+    out->nullable[i] = progs_[i].nullable ? 1 : 0;
     if (progs_[i].max_depth > maxd) maxd = progs_[i].max_depth;
   }
   out->f64_only = 1;
@@ -264,6 +284,8 @@ void ProgramBuilder::finish(ProgramSet* out) const {
   for (size_t s = 0; s < slots_.size(); s++) {
     const DevColumn& c = batch_->cols[size_t(slots_[s])];
     out->cols[s].ptr = c.values;
+    out->cols[s].validity = c.null_count > 0 ? c.validity : nullptr;
+    if (c.null_count > 0) out->has_nulls = 1;
     out->cols[s].dtype = c.dtype;
   }
 }

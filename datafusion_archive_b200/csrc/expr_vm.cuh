@@ -38,6 +38,7 @@ constexpr int kMaxCols = 12;
 
 struct ColRef {
   const void* ptr;
+  const unsigned char* validity;  // LSB-first bitmap re-based to row 0, or null when the column has no nulls
   int dtype;
   int _pad;
 };
@@ -51,11 +52,14 @@ struct ProgramSet {
   int ncols;
   int max_depth;
   int f64_only;  // every operand Float64/Boolean and no CAST: the lean evaluator applies
+  int has_nulls; // some referenced column carries a validity bitmap: kernels use the NULLS evaluator
+  uint8_t nullable[kMaxProgs];  // program result can be null (arrow 0.12 array_ops semantics)
 };
 
 // ---- host side ----------------------------------------------------------------------------
 struct CompiledProgram {
   std::vector<DevInsn> code;
+  bool nullable = false;
   int out_dtype = 0;
   int max_depth = 0;
   bool is_plain_column = false;  // program is exactly [PUSH_COL]
@@ -143,6 +147,16 @@ struct GlobalRows {
     return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
   }
   __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)rows[r]; }
+  // bit r = row r of this thread is non-null in column `slot`
+  __device__ __forceinline__ unsigned col_valid(const ProgramSet& ps, int slot) const {
+    const unsigned char* vb = ps.cols[slot].validity;
+    if (!vb) return (1u << R) - 1u;
+    unsigned m = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++)
+      if (rows[r] >= 0 && ((vb[rows[r] >> 3] >> (rows[r] & 7)) & 1)) m |= 1u << r;
+    return m;
+  }
 };
 template <int R>
 struct StagedTile {
@@ -155,6 +169,7 @@ struct StagedTile {
     return load_elem_generic(stage + col_off[slot], ps.cols[slot].dtype, lrow0 + r * 32);
   }
   __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)(row0 + r * 32); }
+  __device__ __forceinline__ unsigned col_valid(const ProgramSet&, int) const { return (1u << R) - 1u; }  // staged path is null-free
 };
 
 __device__ __forceinline__ void store_elem(void* p, int dtype, long long idx, unsigned long long v) {
@@ -231,9 +246,20 @@ __device__ __forceinline__ unsigned long long cast_value(unsigned long long v, i
 // Returns the value stack top in out[]; bit r of the return value is set when valid row r divided
 // by zero.  With F64ONLY every operand is Float64/Boolean (checked on the host): the machine-type
 // dispatch disappears and only the warp-uniform opcode switch is left.
-template <int DEPTH, int R, bool F64ONLY, class Src>
-__device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog, const Src& src,
-                                                 unsigned long long (&out)[R]) {
+//
+// NULLS: arrow 0.12 array_ops null semantics (restated from the crate; call sites expression.rs:127,216):
+// arithmetic and And/Or yield null when either side is null — the builder's append_null stores the
+// type's default, so the VALUE of a null result is 0 / false, which is what FilterRelation's
+// `filter.value(i)` (filter.rs:86) and update_accumulators' `z.value(row)` (aggregate.rs:561-601) read;
+// comparisons never yield null: nulls are ordered (lt/lt_eq: null on the left -> true; gt/gt_eq: null
+// on the right -> true; eq: both null).  `out_valid` receives the validity bits of the result.
+template <int DEPTH, int R, bool F64ONLY, bool NULLS, class Src>
+__device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int prog, const Src& src,
+                                                   unsigned long long (&out)[R], unsigned& out_valid) {
+  constexpr unsigned ALL = (1u << R) - 1u;
+  unsigned vm[DEPTH];
+#pragma unroll
+  for (int d = 0; d < DEPTH; d++) vm[d] = ALL;
   unsigned long long st[DEPTH][R];
 #pragma unroll
   for (int d = 0; d < DEPTH; d++)
@@ -251,9 +277,12 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
     if (op <= V_PUSH_ROWID) {
       // push
 #pragma unroll
-      for (int d = DEPTH - 1; d > 0; d--)
+      for (int d = DEPTH - 1; d > 0; d--) {
+        if (NULLS) vm[d] = vm[d - 1];
 #pragma unroll
         for (int r = 0; r < R; r++) st[d][r] = st[d - 1][r];
+      }
+      if (NULLS) vm[0] = op == V_PUSH_COL ? src.col_valid(ps, slot) : ALL;
       if (op == V_PUSH_IMM) {
 #pragma unroll
         for (int r = 0; r < R; r++) st[0][r] = imm;
@@ -268,28 +297,40 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
       const int src_dt = ps.insn[pc].aux;
 #pragma unroll
       for (int r = 0; r < R; r++) st[0][r] = cast_value(st[0][r], mt, src_dt, dt);
+      if (NULLS) {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (!((vm[0] >> r) & 1u)) st[0][r] = 0ull;
+      }
     } else {
       unsigned long long rhs[R];
+      unsigned vr = ALL, vl = ALL;
       if (mode == RHS_IMM) {
 #pragma unroll
         for (int r = 0; r < R; r++) rhs[r] = imm;
+        if (NULLS) vl = vm[0];
       } else if (mode == RHS_COL) {
 #pragma unroll
         for (int r = 0; r < R; r++) rhs[r] = src.load(ps, slot, r);
+        if (NULLS) { vl = vm[0]; vr = src.col_valid(ps, slot); }
       } else {
         // pop: rhs = top, lhs = next; shift the stack down by one
 #pragma unroll
         for (int r = 0; r < R; r++) rhs[r] = st[0][r];
+        if (NULLS) { vr = vm[0]; vl = vm[DEPTH > 1 ? 1 : 0]; }
 #pragma unroll
-        for (int d = 0; d < DEPTH - 1; d++)
+        for (int d = 0; d < DEPTH - 1; d++) {
+          if (NULLS) vm[d] = vm[d + 1];
 #pragma unroll
           for (int r = 0; r < R; r++) st[d][r] = st[d + 1][r];
+        }
       }
+      const unsigned both = vl & vr;
       // The (machine type, op) dispatch is hoisted out of the per-row loop: it is warp-uniform and
       // paid once per R rows.  A zero divisor sets the row's bit in badmask (arrow 0.12
       // array_ops::divide returns ArrowError::DivideByZero for ints and floats alike).
 #define DF_ROWS(EXPR) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long a = st[0][r], b = rhs[r]; (void)a; (void)b; st[0][r] = (EXPR); }
-#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if (COND) badmask |= 1u << r; }
+#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if ((COND) && (!NULLS || ((both >> r) & 1u))) badmask |= 1u << r; }
       switch (F64ONLY ? (op >= V_AND ? (int)MT_BOOL : (int)MT_F64) : mt) {
         case MT_F64:
           switch (op) {
@@ -361,11 +402,45 @@ __device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog,
       }
 #undef DF_ROWS
 #undef DF_DIVCHK
+      if (NULLS) {
+        if (op >= V_EQ && op <= V_GE) {
+          // comparisons: never null; a null operand is ordered, not propagated
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (!((both >> r) & 1u)) {
+              const bool ln = !((vl >> r) & 1u), rn = !((vr >> r) & 1u);
+              bool v;
+              switch (op) {
+                case V_EQ: v = ln && rn; break;
+                case V_NE: v = !(ln && rn); break;
+                case V_LT: case V_LE: v = ln; break;
+                default: v = rn; break;
+              }
+              st[0][r] = v ? 1ull : 0ull;
+            }
+          }
+          vm[0] = ALL;
+        } else {
+          // arithmetic, And, Or: null if either side is null; append_null stores the default value
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (!((both >> r) & 1u)) st[0][r] = 0ull;
+          vm[0] = both;
+        }
+      }
     }
   }
 #pragma unroll
   for (int r = 0; r < R; r++) out[r] = st[0][r];
+  out_valid = NULLS ? vm[0] : ALL;
   return badmask & src.valid;
+}
+
+template <int DEPTH, int R, bool F64ONLY, class Src>
+__device__ __forceinline__ unsigned eval_program(const ProgramSet& ps, int prog, const Src& src,
+                                                 unsigned long long (&out)[R]) {
+  unsigned ov;
+  return eval_program_n<DEPTH, R, F64ONLY, false>(ps, prog, src, out, ov);
 }
 #endif  // __CUDACC__
 

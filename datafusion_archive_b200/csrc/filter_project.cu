@@ -16,7 +16,12 @@
 
 namespace dfgpu {
 
-template <int DEPTH>
+// NULLS: some referenced column has a validity bitmap.  The predicate is evaluated with arrow's null
+// semantics (a null And/Or result reads as false, like `filter.value(i)` in filter.rs:86).  With a
+// predicate the projections then see null-free arrays, exactly like the reference: `fn filter` copies
+// values and drops the bitmap (filter.rs:83-91) before ProjectRelation runs.  Without a predicate the
+// projections run on the original arrays and their validity is written out (32 rows per ballot word).
+template <int DEPTH, bool NULLS>
 __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_constant__ FPParams p) {
   __shared__ int s_tile;
   __shared__ unsigned s_wcount[FP_ITEMS * FP_WARPS];
@@ -49,7 +54,8 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
       }
       if (p.has_pred) {
         unsigned long long v[FP_R];
-        unsigned b = eval_program<DEPTH, FP_R, false>(p.ps, 0, src, v);
+        unsigned ov;
+        unsigned b = eval_program_n<DEPTH, FP_R, false, NULLS>(p.ps, 0, src, v, ov);
         bad = bad || (b != 0);
 #pragma unroll
         for (int r = 0; r < FP_R; r++)
@@ -130,7 +136,23 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
           if (row < p.nrows) src.valid |= 1u << r;
         }
         unsigned long long v[FP_R];
-        const unsigned b = eval_program<DEPTH, FP_R, false>(p.ps, prog, src, v);
+        unsigned ov = (1u << FP_R) - 1u;
+        unsigned b;
+        if (NULLS && !p.has_pred) b = eval_program_n<DEPTH, FP_R, false, true>(p.ps, prog, src, v, ov);
+        else b = eval_program<DEPTH, FP_R, false>(p.ps, prog, src, v);
+        if (NULLS && !p.has_pred && p.out_valid[q]) {
+#pragma unroll
+          for (int r = 0; r < FP_R; r++) {
+            const bool inb = (src.valid >> r) & 1u;
+            const unsigned vb = __ballot_sync(0xffffffffu, inb && ((ov >> r) & 1u));
+            const unsigned ib = __ballot_sync(0xffffffffu, inb);
+            if (lane == 0 && ib) {
+              p.out_valid[q][src.rows[r] >> 5] = vb;  // the warp's 32 rows are consecutive and 32-aligned
+              const unsigned nn = __popc(ib & ~vb);
+              if (nn) atomicAdd(&p.null_counts[q], (unsigned long long)nn);
+            }
+          }
+        }
 #pragma unroll
         for (int r = 0; r < FP_R; r++) {
           const int j = c * FP_R + r;
@@ -151,15 +173,15 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
   }
 }
 
-template <int DEPTH>
+template <int DEPTH, bool NULLS = false>
 static void launch_fp(dfgpu_ctx* ctx, const FPParams& p) {
   int per_sm = 0;
-  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_project<DEPTH>, FP_THREADS, 0));
+  DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_project<DEPTH, NULLS>, FP_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)ctx->sm_count * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
   const int ps = ctx->prof_begin();
-  k_filter_project<DEPTH><<<(unsigned)grid, FP_THREADS, 0, ctx->stream>>>(p);
+  k_filter_project<DEPTH, NULLS><<<(unsigned)grid, FP_THREADS, 0, ctx->stream>>>(p);
   DF_CUDA(cudaGetLastError());
   ctx->prof_end(ps);
   ctx->launches++;
@@ -235,8 +257,6 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       if (!is_numeric(p.ps.cols[s].dtype))
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("expressions over ") + dtype_name(p.ps.cols[s].dtype) + " columns are not supported on the GPU path yet");
     }
-    for (const auto& c : batch->cols)
-      if (c.null_count > 0) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
     if (p.ps.max_depth > 8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression too deep (register stack depth > 8)");
 
     auto res = std::make_unique<dfgpu_result>();
@@ -291,6 +311,23 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     p.out_count = ctx->d_scratch + 0;
     p.ticket = (unsigned*)(ctx->d_scratch + 1);
     p.err_flag = (unsigned*)(ctx->d_scratch + 2);
+    // validity outputs: only a query WITHOUT a predicate can emit nulls (see k_filter_project)
+    memset(p.out_valid, 0, sizeof(p.out_valid));
+    p.null_counts = ctx->d_scratch + 32;
+    std::vector<int> valid_of_out(size_t(nproj), -1);  // result column -> kernel program with a validity buffer
+    if (p.ps.has_nulls && !has_pred) {
+      DF_CUDA(cudaMemsetAsync(ctx->d_scratch + 32, 0, kMaxProgs * 8, ctx->stream));
+      for (int i = 0; i < nproj; i++) {
+        const int k = out_kind[size_t(i)];
+        if (k >= 0 && p.ps.nullable[k]) {
+          const size_t vbytes = size_t((n + 31) / 32) * 4;
+          res->cols[size_t(i)].validity = (uint8_t*)ctx->alloc(vbytes);
+          DF_CUDA(cudaMemsetAsync(res->cols[size_t(i)].validity, 0, vbytes, ctx->stream));
+          p.out_valid[k] = (unsigned*)res->cols[size_t(i)].validity;
+          valid_of_out[size_t(i)] = k;
+        }
+      }
+    }
     // fast shapes (see FPParams): straight from the lowered bytecode
     auto fast_of = [&](int prog, bool is_pred) {
       FastOp f;
@@ -351,7 +388,10 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       if (ok) p.pred_fast = fp;
     }
     for (int i = 0; i < nkern; i++) p.proj_fast[i] = fast_of(i + has_pred, false);
-    if (ctx->force_direct_kernel || !launch_fp_tma(ctx, p)) {
+    if (p.ps.has_nulls) {
+      p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
+      launch_fp<8, true>(ctx, p);  // the null-aware evaluator lives in the direct kernel only
+    } else if (ctx->force_direct_kernel || !launch_fp_tma(ctx, p)) {
       p.ntiles = int((n + FP_TILE - 1) / FP_TILE);
       const int d = p.ps.max_depth;
       if (d <= 1) launch_fp<1>(ctx, p);
@@ -360,14 +400,37 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       else launch_fp<8>(ctx, p);
     }
     DF_CUDA(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p.ps.has_nulls && !has_pred)
+      DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 32, ctx->d_scratch + 32, kMaxProgs * 8, cudaMemcpyDeviceToHost, ctx->stream));
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->free(status);
+    for (int i = 0; i < nproj; i++) {
+      DevColumn& c = res->cols[size_t(i)];
+      if (valid_of_out[size_t(i)] >= 0) {
+        c.null_count = (int64_t)ctx->h_scratch[32 + valid_of_out[size_t(i)]];
+        if (c.null_count == 0) {
+          ctx->free(c.validity);
+          c.validity = nullptr;
+        }
+      }
+    }
     if ((unsigned)ctx->h_scratch[2] != 0) fail(DFGPU_ERR_ARROW, "DivideByZero");
     res->nrows = has_pred ? (int64_t)ctx->h_scratch[0] : n;
     for (int i = 0; i < nproj; i++)
       if (out_kind[size_t(i)] < 0)
         gather_utf8(ctx, batch->cols[size_t(-1 - out_kind[size_t(i)])], (const unsigned long long*)scratch.cols[0].values, res->nrows,
                     &res->cols[size_t(i)]);
+    if (!has_pred)
+      for (int i = 0; i < nproj; i++)
+        if (out_kind[size_t(i)] < 0) {  // Utf8 column passed through untouched keeps its validity (expression.rs:313)
+          const DevColumn& srcc = batch->cols[size_t(-1 - out_kind[size_t(i)])];
+          if (srcc.null_count > 0) {
+            const size_t vb = size_t(n + 7) / 8;
+            res->cols[size_t(i)].validity = (uint8_t*)ctx->alloc(vb);
+            DF_CUDA(cudaMemcpyAsync(res->cols[size_t(i)].validity, srcc.validity, vb, cudaMemcpyDeviceToDevice, ctx->stream));
+            res->cols[size_t(i)].null_count = srcc.null_count;
+          }
+        }
     if (any_utf8) DF_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = res.release();
   });

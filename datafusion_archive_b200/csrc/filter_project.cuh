@@ -30,6 +30,10 @@ struct FastPred {
 struct FPParams {
   ProgramSet ps;  // program 0 = predicate when has_pred, projections follow
   void* out[kMaxProgs];
+  // no-predicate queries over nullable inputs: per-projection validity bitmap (32 rows per word) and
+  // null counter; null when the projection cannot produce nulls
+  unsigned* out_valid[kMaxProgs];
+  unsigned long long* null_counts;  // [kMaxProgs]
   long long nrows;
   int ntiles;
   int has_pred;

@@ -341,6 +341,38 @@ std::optional<RecordBatch> GpuFilterProjectRelation::next() {
   std::vector<const dfgpu_insn*> pp;
   std::vector<int> pl;
   for (auto& p : progs) { pp.push_back(p.data()); pl.push_back(int(p.size())); }
+  // Large all-numeric batches: host buffers in, pinned host buffers out, with upload / kernel /
+  // download overlapped by row-range chunk inside the library; the result columns are wrapped
+  // zero-copy (the pinned block lives as long as the RecordBatch).
+  bool numeric_only = batch->num_rows >= (4ll << 20);
+  for (size_t c : pr.cols) numeric_only = numeric_only && datatype_width(batch->columns[c]->data_type) > 0 && batch->columns[c]->null_count == 0;
+  if (numeric_only) {
+    std::vector<dfgpu_col> cols;
+    for (size_t c : pr.cols) cols.push_back(batch->columns[c]->view());
+    dfgpu_result* raw = nullptr;
+    GPU_CHECK(dfgpu_filter_project_host(gpu_, cols.data(), int(cols.size()), pred.data(), int(pred.size()), pp.data(), pl.data(), int(pp.size()), 0, &raw));
+    std::shared_ptr<void> owner(raw, [](void* p) { dfgpu_result_free(static_cast<dfgpu_result*>(p)); });
+    RecordBatch out;
+    out.schema = schema_;
+    int64_t nrows = 0;
+    int ncols = 0;
+    GPU_CHECK(dfgpu_result_shape(raw, &nrows, &ncols));
+    out.num_rows = nrows;
+    for (int i = 0; i < ncols; i++) {
+      auto a = std::make_shared<Array>();
+      int32_t dt = 0;
+      const void* hp = nullptr;
+      GPU_CHECK(dfgpu_result_col_dtype(raw, i, &dt));
+      GPU_CHECK(dfgpu_result_col_host_ptr(raw, i, &hp));
+      a->data_type = dt;
+      a->len = nrows;
+      a->values = hp;
+      a->values_bytes = nrows * datatype_width(dt);
+      a->owner = owner;
+      out.columns.push_back(a);
+    }
+    return out;
+  }
   BatchGuard b;
   b.b = upload(gpu_, *batch, pr);
   ResultGuard r;

@@ -26,6 +26,7 @@ struct Array {
   const uint8_t* validity = nullptr;
   const int32_t* offsets = nullptr;
   int64_t values_bytes = 0;  // Utf8 byte buffer size
+  std::shared_ptr<void> owner;  // keeps library-owned (pinned) result memory alive for zero-copy columns
   dfgpu_col view() const;    // borrowed Arrow view for the C ABI
 };
 using ArrayRef = std::shared_ptr<Array>;

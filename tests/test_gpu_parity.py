@@ -479,3 +479,79 @@ def test_c4_full_size_properties(ctx):
     assert np.array_equal(got[0], inv[order])
     assert np.array_equal(got[2], cnt[order].astype(np.uint64))
     np.testing.assert_allclose(got[1], sm[order], rtol=SUM_RTOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# nulls: arrow 0.12 array_ops semantics as the reference's operators see them (oracle restates them)
+# ---------------------------------------------------------------------------------------------
+def nullable(values, valid):
+    """pyarrow array over OUR buffers, so the bytes under null slots are known to both sides."""
+    import pyarrow as pa
+    values = np.ascontiguousarray(values)
+    bits = np.packbits(np.asarray(valid, dtype=bool), bitorder="little")
+    return pa.Array.from_buffers(pa.from_numpy_dtype(values.dtype), len(values), [pa.py_buffer(bits.tobytes()), pa.py_buffer(values.tobytes())])
+
+
+def unpack(c):
+    return c if isinstance(c, tuple) else (c, np.ones(len(c), dtype=bool))
+
+
+def assert_nullable_equal(got, exp):
+    assert len(got) == len(exp)
+    for g, e in zip(got, exp):
+        (gv, gm), (ev, em) = unpack(g), unpack(e)
+        assert gv.dtype == ev.dtype and np.array_equal(gm, em)
+        assert np.array_equal(gv[gm].view(np.uint8), ev[em].view(np.uint8))
+
+
+def test_nulls_filter_and_projection(ctx):
+    rng = np.random.default_rng(41)
+    n = 150_001
+    a, b = rng.random(n), rng.random(n)
+    i = rng.integers(-100, 100, n, dtype=np.int64)
+    va, vb, vi = rng.random(n) > 0.2, rng.random(n) > 0.3, rng.random(n) > 0.1
+    arrays = [nullable(a, va), nullable(b, vb), nullable(i, vi), a.copy()]
+    preds = [col(0) > lit(0.5), col(0) < lit(0.5), col(0) < col(1), col(0) >= col(1), col(0).eq(col(1)), col(0).not_eq(col(1)),
+             (col(0) > lit(0.3)) & (col(1) < lit(0.6)), (col(0) > lit(0.9)) | (col(1) <= col(0)), (col(0) + col(1)) > lit(1.0),
+             col(2) > lit(0)]
+    O.set_extensions(filter_all_primitives=True)
+    try:
+        for pred in preds:
+            proj = [col(0), col(1), col(0) * col(1), col(2), col(3)]
+            assert_nullable_equal(gpu_fp(ctx, arrays, pred, proj), O.filter_project(arrays, pred, proj))
+        # no predicate: projections keep / produce nulls
+        proj = [col(0), col(0) + col(1), col(0) * lit(2.0), col(2) - col(2), col(0) < col(1), col(3), col(2).cast(A.INT32)]
+        proj_num = [p for p in proj if p is not proj[4]]  # Boolean outputs are not on the GPU path
+        assert_nullable_equal(gpu_fp(ctx, arrays, None, proj_num), O.filter_project(arrays, None, proj_num))
+    finally:
+        O.set_extensions(filter_all_primitives=False)
+
+
+def test_nulls_aggregates(ctx):
+    rng = np.random.default_rng(43)
+    n = 120_000
+    k = rng.integers(0, 500, n, dtype=np.int32)
+    v, w = rng.random(n), rng.random(n)
+    vk, vv, vw = rng.random(n) > 0.1, rng.random(n) > 0.4, rng.random(n) > 0.5
+    arrays = [nullable(k, vk), nullable(v, vv), nullable(w, vw)]
+    aggs = [AggregateFunction("sum", col(1)), AggregateFunction("min", col(1)), AggregateFunction("max", col(1)),
+            AggregateFunction("count", col(1)), AggregateFunction("count", col(2))]
+    got = gpu_agg(ctx, arrays, [col(0)], aggs)
+    exp = O.aggregate(arrays, [col(0)], aggs)
+    check_groupby(got, exp, 1, set(), {1})
+    # arithmetic over nullable columns as an aggregate argument (null reads as 0, aggregate.rs:561-601): small input,
+    # the reference re-evaluates the argument per row
+    m = 3000
+    small = [nullable(k[:m], vk[:m]), nullable(v[:m], vv[:m]), nullable(w[:m], vw[:m])]
+    aggs2 = [AggregateFunction("sum", col(1) + col(2)), AggregateFunction("count", col(1) + col(2))]
+    check_groupby(gpu_agg(ctx, small, [col(0)], aggs2), O.aggregate(small, [col(0)], aggs2), 1, set(), {1})
+    # no GROUP BY: array_ops min/max/sum skip nulls
+    aggs3 = [AggregateFunction("min", col(1)), AggregateFunction("max", col(1)), AggregateFunction("sum", col(1)), AggregateFunction("count", col(1))]
+    g, e = gpu_agg(ctx, arrays, [], aggs3, nbatches=3), O.aggregate(arrays, [], aggs3, batch_size=40_000)
+    assert g[0][0] == e[0][0] and g[1][0] == e[1][0] and g[3][0] == e[3][0] == int(vv.sum())
+    assert abs(g[2][0] - e[2][0]) <= SUM_RTOL * abs(e[2][0])
+    # all-null column: MIN/MAX/SUM are null, COUNT is 0
+    allnull = [nullable(v[:1000], np.zeros(1000, dtype=bool))]
+    g = gpu_agg(ctx, allnull, [], [AggregateFunction("sum", col(0)), AggregateFunction("min", col(0)), AggregateFunction("count", col(0))])
+    assert not unpack(g[0])[1][0] and not unpack(g[1])[1][0]
+    assert unpack(g[2])[0][0] == 0 and unpack(g[2])[1][0]

@@ -124,6 +124,17 @@ def test_memory_tables_baseline_queries(ctx):
     assert np.array_equal(k2[o1], e2[0][o2]) and np.array_equal(mx[o1], e2[1][o2])
 
 
+def test_large_batch_takes_pipelined_path(ctx):
+    # >= 4 Mi rows, numeric columns: GpuFilterProjectRelation::next goes through dfgpu_filter_project_host
+    n = 5_000_000
+    arrays, pred, proj = workloads.c3(n, seed=77)
+    ctx.register_memory("big", list(zip("abcd", arrays)))
+    got = ctx.sql("SELECT a+b, a*b FROM big WHERE b<a").collect()
+    a, b = arrays[0], arrays[1]
+    m = b < a
+    assert len(got) == 1 and np.array_equal(got[0][0], (a + b)[m]) and np.array_equal(got[0][1], (a * b)[m])
+
+
 def test_error_mapping(ctx):
     register_cities(ctx)
     for sql, code, msg in [
