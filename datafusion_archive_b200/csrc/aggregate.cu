@@ -14,6 +14,9 @@
 
 namespace dfgpu {
 
+void utf8_hash(dfgpu_ctx* ctx, const DevColumn& src, long long n, unsigned long long* d_out);
+void gather_utf8_multi(dfgpu_ctx* ctx, const Utf8Source* d_srcs, const unsigned long long* d_idx, long long nsel, DevColumn* out);
+
 constexpr int AG_THREADS = 256;
 constexpr int AG_R = 4;
 constexpr int AG_TILE = AG_THREADS * AG_R;
@@ -500,6 +503,45 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
   if (new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
 }
 
+// Utf8 GROUP BY keys are grouped by a 64-bit hash of the string; accumulator `rep_agg` holds the
+// earliest (source << 40 | row) of each group.  Every row's string must equal its group's
+// representative string, otherwise two different strings collided on the hash.
+struct VerifyParams {
+  const unsigned long long* hashes;
+  long long n;
+  TableLayout t;
+  long long cap;
+  int rep_agg;
+  const int* off;
+  const unsigned char* bytes;
+  const Utf8Source* srcs;
+  unsigned long long* flag;
+};
+__global__ void __launch_bounds__(256) k_utf8_group_verify(const __grid_constant__ VerifyParams p) {
+  const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = p.hashes[i];
+    long long slot = p.cap;
+    if (key != EMPTY_KEY) {
+      unsigned long long h = mix64(key) & hmask;
+      for (;;) {
+        const unsigned long long cur = __ldcg(p.t.key((long long)h));
+        if (cur == key) { slot = (long long)h; break; }
+        if (cur == EMPTY_KEY) { slot = -1; break; }
+        h = (h + 1ull) & hmask;
+      }
+    }
+    if (slot < 0) { *p.flag = 2ull; continue; }
+    const unsigned long long rep = *p.t.val(slot, p.rep_agg);
+    const Utf8Source& sc = p.srcs[rep >> UTF8_SRC_SHIFT];
+    const long long r = (long long)(rep & ((1ull << UTF8_SRC_SHIFT) - 1ull));
+    const int s = p.off[i], len = p.off[i + 1] - s, s2 = sc.off[r], len2 = sc.off[r + 1] - s2;
+    bool same = len == len2;
+    for (int b = 0; same && b < len; b++) same = p.bytes[s + b] == sc.bytes[s2 + b];
+    if (!same) *p.flag = 1ull;
+  }
+}
+
 // fill the table with empty keys and accumulator identities
 struct InitParams {
   TableLayout t;
@@ -539,6 +581,13 @@ struct dfgpu_aggstate {
   TableLayout t{nullptr, 0, 0, 0};
   bool aos = false;
   bool use_front = false;  // route rows through the per-CTA shared-memory front table
+  // Utf8 GROUP BY key (aggregate.rs:842-847): grouped by a 64-bit string hash; the last accumulator is a
+  // hidden MIN(source << 40 | row) = representative row of the group; the key columns of all batches are
+  // retained so the representatives' strings can be gathered at finish
+  bool utf8_key = false;
+  std::vector<void*> utf8_owned;         // retained offsets / bytes buffers (device)
+  std::vector<Utf8Source> utf8_srcs;     // host copy of the source table
+  Utf8Source* d_utf8_srcs = nullptr;
   bool saw_nulls = false;  // some batch went through the null-aware reduce: per-aggregate non-null counts are on the device
   std::vector<long long> nonnull_host = std::vector<long long>(8, 0);
   unsigned long long* d_counters = nullptr;  // 8 x u64
@@ -551,6 +600,8 @@ struct dfgpu_aggstate {
     if (ctx) {
       ctx->free(t.base);
       ctx->free(d_counters);
+      for (void* p : utf8_owned) ctx->free(p);
+      ctx->free(d_utf8_srcs);
     }
   }
 };
@@ -739,17 +790,36 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     memset(&p, 0, sizeof(p));
     ProgramBuilder pb(batch);
     std::vector<int> kdt;
-    for (int k = 0; k < st->nkeys; k++) {
-      int pi = pb.add(st->key_progs[size_t(k)].data(), int(st->key_progs[size_t(k)].size()), "GROUP BY expression");
-      int dt = pb.out_dtype(pi);
-      if (dt == DFGPU_UTF8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys are not supported on the GPU path yet");
-      if (!is_int(dt)) fail(DFGPU_ERR_EXECUTION, "Unsupported GROUP BY data type");  // aggregate.rs:848-850
-      kdt.push_back(dt);
+    // a single plain Utf8 column as the key: group by a 64-bit hash of the strings (see dfgpu_aggstate)
+    const DevColumn* ukey = nullptr;
+    if (st->nkeys == 1 && st->key_progs[0].size() == 1 && st->key_progs[0][0].op == DFGPU_OP_COL && st->key_progs[0][0].col >= 0 &&
+        size_t(st->key_progs[0][0].col) < batch->cols.size() && batch->cols[size_t(st->key_progs[0][0].col)].dtype == DFGPU_UTF8)
+      ukey = &batch->cols[size_t(st->key_progs[0][0].col)];
+    unsigned long long* d_hash = nullptr;
+    struct HashFree { dfgpu_ctx* c; unsigned long long** p; ~HashFree() { c->free(*p); } } hash_free{ctx, &d_hash};
+    if (ukey) {
+      if (st->typed && !st->utf8_key) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
+      if (!st->typed && st->naggs >= kMaxAggs) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY key with " + std::to_string(kMaxAggs) + " aggregates");
+      if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys with a multi-GPU communicator");
+      if (st->utf8_srcs.size() >= (1u << 20)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than 2^20 batches with a Utf8 GROUP BY key");
+      d_hash = (unsigned long long*)ctx->alloc(size_t(batch->nrows > 0 ? batch->nrows : 1) * 8);
+      utf8_hash(ctx, *ukey, batch->nrows, d_hash);
+      pb.add_synthetic_column(d_hash, DFGPU_UINT64);
+      kdt.push_back(DFGPU_UINT64);
+    } else {
+      for (int k = 0; k < st->nkeys; k++) {
+        int pi = pb.add(st->key_progs[size_t(k)].data(), int(st->key_progs[size_t(k)].size()), "GROUP BY expression");
+        int dt = pb.out_dtype(pi);
+        if (dt == DFGPU_UTF8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys are supported as a single plain column only");
+        if (!is_int(dt)) fail(DFGPU_ERR_EXECUTION, "Unsupported GROUP BY data type");  // aggregate.rs:848-850
+        kdt.push_back(dt);
+      }
     }
+    const int user_aggs = st->utf8_key ? st->naggs - 1 : st->naggs;  // the hidden representative is appended below
     std::vector<AggDesc> descs;
-    std::vector<int> agg_arg(size_t(st->naggs), 0);
+    std::vector<int> agg_arg(size_t(user_aggs), 0);
     int nargs = 0;
-    for (int a = 0; a < st->naggs; a++) {
+    for (int a = 0; a < user_aggs; a++) {
       // identical argument expressions are compiled (and evaluated) once
       int same = -1;
       for (int b = 0; b < a && same < 0; b++) {
@@ -777,6 +847,34 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         fail(DFGPU_ERR_EXECUTION, "unexpected type when creating array from aggregate map");
       d.out_dtype = uint8_t(odt);
       descs.push_back(d);
+    }
+    if (ukey) {
+      // hidden accumulator: MIN(source << 40 | row)
+      pb.add_rowid_plus((unsigned long long)st->utf8_srcs.size() << UTF8_SRC_SHIFT);
+      agg_arg.push_back(nargs++);
+      AggDesc d;
+      d.func = DFGPU_AGG_MIN;
+      d.mtype = MT_U;
+      d.dtype = DFGPU_UINT64;
+      d.out_dtype = DFGPU_UINT64;
+      descs.push_back(d);
+      if (!st->typed) {
+        st->utf8_key = true;
+        st->naggs += 1;
+      }
+      // retain this batch's key column: representatives are gathered from it at finish
+      const size_t ob = size_t(batch->nrows + 1) * 4, vb = ukey->values_bytes ? ukey->values_bytes : 1;
+      int* off = (int*)ctx->alloc(ob);
+      unsigned char* bytes = (unsigned char*)ctx->alloc(vb);
+      DF_CUDA(cudaMemcpyAsync(off, ukey->offsets, ob, cudaMemcpyDeviceToDevice, ctx->stream));
+      if (ukey->values_bytes) DF_CUDA(cudaMemcpyAsync(bytes, ukey->values, ukey->values_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+      st->utf8_owned.push_back(off);
+      st->utf8_owned.push_back(bytes);
+      st->utf8_srcs.push_back(Utf8Source{off, bytes});
+      ctx->free(st->d_utf8_srcs);
+      st->d_utf8_srcs = (Utf8Source*)ctx->alloc(st->utf8_srcs.size() * sizeof(Utf8Source));
+      DF_CUDA(cudaMemcpyAsync(st->d_utf8_srcs, st->utf8_srcs.data(), st->utf8_srcs.size() * sizeof(Utf8Source), cudaMemcpyHostToDevice, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));  // utf8_srcs may reallocate on the next batch
     }
     if (!st->typed) {
       st->key_dtypes = kdt;
@@ -908,6 +1006,27 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         table_grow(st, std::max(st->cap, next_pow2(st->ngroups * 8)));
       }
     }
+    if (ukey) {
+      VerifyParams vp;
+      memset(&vp, 0, sizeof(vp));
+      vp.hashes = d_hash;
+      vp.n = batch->nrows;
+      vp.t = st->t;
+      vp.cap = st->cap;
+      vp.rep_agg = st->naggs - 1;
+      vp.off = ukey->offsets;
+      vp.bytes = (const unsigned char*)ukey->values;
+      vp.srcs = st->d_utf8_srcs;
+      vp.flag = st->d_counters + 5;
+      DF_CUDA(cudaMemsetAsync(st->d_counters + 5, 0, 8, ctx->stream));
+      k_utf8_group_verify<<<grid_for(ctx, batch->nrows, 256, 8), 256, 0, ctx->stream>>>(vp);
+      DF_CUDA(cudaGetLastError());
+      ctx->launches++;
+      DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 12, st->d_counters + 5, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->h_scratch[12] == 1ull) fail(DFGPU_ERR_INTERNAL, "two different Utf8 GROUP BY keys share a 64-bit hash (p < 1e-7 per 1e6 distinct keys)");
+      if (ctx->h_scratch[12]) fail(DFGPU_ERR_INTERNAL, "Utf8 GROUP BY verification could not find a group");
+    }
   });
 }
 
@@ -1028,12 +1147,21 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     cp.nkeys = st->nkeys;
     cp.naggs = st->naggs;
     cp.raw = 0;
+    dfgpu_result hidden;  // RAII: hash-key and representative columns of a Utf8-keyed aggregate
+    hidden.ctx = ctx;
     for (int k = 0; k < st->nkeys; k++) {  // group columns first (aggregate.rs:890-925)
       DevColumn c;
       c.dtype = st->key_dtypes[size_t(k)];
       c.values_bytes = alloc_n * size_t(dtype_width(c.dtype));
       c.values = ctx->alloc(c.values_bytes);
-      res->cols.push_back(c);
+      if (st->utf8_key) {
+        hidden.cols.push_back(c);
+        DevColumn u;
+        u.dtype = DFGPU_UTF8;  // filled by the gather below
+        res->cols.push_back(u);
+      } else {
+        res->cols.push_back(c);
+      }
       cp.out_keys[k] = c.values;
       cp.key_dtype[k] = c.dtype;
       cp.key_mask[k] = st->key_mask[size_t(k)];
@@ -1044,7 +1172,8 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       c.dtype = st->descs[size_t(a)].out_dtype;
       c.values_bytes = alloc_n * size_t(dtype_width(c.dtype));
       c.values = ctx->alloc(c.values_bytes);
-      res->cols.push_back(c);
+      if (st->utf8_key && a == st->naggs - 1) hidden.cols.push_back(c);  // representative rows: not a result column
+      else res->cols.push_back(c);
       cp.out_vals[a] = c.values;
       cp.aggs[a] = st->descs[size_t(a)];
     }
@@ -1057,6 +1186,8 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
     res->nrows = cnt;
+    if (st->utf8_key)  // key strings = the representatives' strings, in output order
+      gather_utf8_multi(ctx, st->d_utf8_srcs, (const unsigned long long*)hidden.cols[1].values, cnt, &res->cols[0]);
     if (st->nkeys == 0) {
       // an aggregate that saw no non-null input is null (array_from_scalar!, aggregate.rs:641-643)
       std::vector<long long> nonnull = st->nonnull_host;

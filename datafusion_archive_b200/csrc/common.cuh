@@ -110,6 +110,15 @@ struct DevColumn {
   int64_t null_count = 0;
 };
 
+namespace dfgpu {
+// one Utf8 column on the device (arrow 0.12 BinaryArray): the unit of the multi-source string gather
+struct Utf8Source {
+  const int* off;
+  const unsigned char* bytes;
+};
+constexpr int UTF8_SRC_SHIFT = 40;  // gather index = (source << 40) | row
+}  // namespace dfgpu
+
 struct dfgpu_batch {
   dfgpu_ctx* ctx = nullptr;
   int64_t nrows = 0;

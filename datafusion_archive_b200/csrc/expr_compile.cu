@@ -258,6 +258,45 @@ int ProgramBuilder::add_rowid() {
   return int(progs_.size()) - 1;
 }
 
+int ProgramBuilder::add_rowid_plus(unsigned long long bias) {
+  CompiledProgram cp;
+  DevInsn di;
+  memset(&di, 0, sizeof(di));
+  di.op = V_PUSH_ROWID;
+  di.dtype = DFGPU_UINT64;
+  di.mtype = MT_U;
+  cp.code.push_back(di);
+  memset(&di, 0, sizeof(di));
+  di.op = V_ADD;
+  di.mode = RHS_IMM;
+  di.dtype = DFGPU_UINT64;
+  di.mtype = MT_U;
+  di.imm = bias;
+  cp.code.push_back(di);
+  cp.out_dtype = DFGPU_UINT64;
+  cp.max_depth = 1;
+  progs_.push_back(std::move(cp));
+  return int(progs_.size()) - 1;
+}
+
+int ProgramBuilder::add_synthetic_column(const void* dptr, int dtype) {
+  if (int(slots_.size()) >= kMaxCols) fail(DFGPU_ERR_NOT_IMPLEMENTED, "too many distinct columns");
+  synth_.push_back(Synth{dptr, dtype});
+  slots_.push_back(-int(synth_.size()));  // -1 - k
+  CompiledProgram cp;
+  DevInsn di;
+  memset(&di, 0, sizeof(di));
+  di.op = V_PUSH_COL;
+  di.slot = int16_t(slots_.size() - 1);
+  di.dtype = uint8_t(dtype);
+  di.mtype = mtype_of(dtype);
+  cp.code.push_back(di);
+  cp.out_dtype = dtype;
+  cp.max_depth = 1;
+  progs_.push_back(std::move(cp));
+  return int(progs_.size()) - 1;
+}
+
 void ProgramBuilder::finish(ProgramSet* out) const {
   memset(out, 0, sizeof(*out));
   if (int(progs_.size()) > kMaxProgs)
@@ -282,6 +321,13 @@ void ProgramBuilder::finish(ProgramSet* out) const {
   out->ncols = int(slots_.size());
   out->max_depth = maxd;
   for (size_t s = 0; s < slots_.size(); s++) {
+    if (slots_[s] < 0) {
+      const Synth& sy = synth_[size_t(-1 - slots_[s])];
+      out->cols[s].ptr = sy.ptr;
+      out->cols[s].validity = nullptr;
+      out->cols[s].dtype = sy.dtype;
+      continue;
+    }
     const DevColumn& c = batch_->cols[size_t(slots_[s])];
     out->cols[s].ptr = c.values;
     out->cols[s].validity = c.null_count > 0 ? c.validity : nullptr;

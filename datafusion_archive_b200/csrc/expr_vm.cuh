@@ -73,6 +73,10 @@ class ProgramBuilder {
   int add(const dfgpu_insn* p, int n, const char* what);
   // Program yielding the global row number (UInt64): the gather index for variable-width columns.
   int add_rowid();
+  // Program yielding `bias + global row number` (UInt64).
+  int add_rowid_plus(unsigned long long bias);
+  // Program that just reads a device array which is not a column of the batch (e.g. key hashes).
+  int add_synthetic_column(const void* dptr, int dtype);
   int out_dtype(int prog) const { return progs_[size_t(prog)].out_dtype; }
   const CompiledProgram& prog(int i) const { return progs_[size_t(i)]; }
   int nprogs() const { return int(progs_.size()); }
@@ -83,7 +87,9 @@ class ProgramBuilder {
  private:
   const dfgpu_batch* batch_;
   std::vector<CompiledProgram> progs_;
-  std::vector<int> slots_;  // slot -> batch column index
+  std::vector<int> slots_;  // slot -> batch column index, or -1 - k for synthetic column k
+  struct Synth { const void* ptr; int dtype; };
+  std::vector<Synth> synth_;
 };
 
 MType mtype_of(int dtype);

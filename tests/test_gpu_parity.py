@@ -35,7 +35,7 @@ def gpu_fp(ctx, arrays, pred, proj):
 
 def gpu_agg(ctx, arrays, keys, aggs, nbatches=1, expected=0):
     n = len(arrays[0])
-    bounds = np.linspace(0, n, nbatches + 1).astype(int)
+    bounds = [int(x) for x in np.linspace(0, n, nbatches + 1)]
     batches = [ctx.upload([a[bounds[i]:bounds[i + 1]] for a in arrays]) for i in range(nbatches)]
     try:
         r = ctx.aggregate(batches, keys, aggs, expected)
@@ -366,6 +366,33 @@ def test_groupby_high_cardinality_layouts(ctx):
     # two batches: the second one finds the table already converted
     got = sort_by_key(gpu_agg(ctx, [k, v], [col(0)], aggs, nbatches=2))
     assert np.array_equal(got[0], uk) and np.array_equal(got[4], np.bincount(inv).astype(np.uint64))
+
+
+def test_golden_group_by_string_min_max(ctx, golden, fmt_f64):
+    # tests/sql.rs:55-67: GROUP BY a Utf8 column
+    t = golden["aggregate_test_2"]
+    out = gpu_agg(ctx, [t["a"], np.array(t["b"])], [col(0)], [AggregateFunction("min", col(1)), AggregateFunction("max", col(1))])
+    got = sorted('"%s"\t%s\t%s\n' % (a, fmt_f64(b), fmt_f64(c)) for a, b, c in zip(*out))
+    assert got == sorted(golden["csv_query_group_by_string_min_max"]["expected"].splitlines(True))
+
+
+def test_groupby_utf8_keys_vs_oracle(ctx):
+    rng = np.random.default_rng(51)
+    n = 120_000
+    vocab = ["", "a", "b", "ab", "ba", "London, UK", "x" * 33] + ["k%05d" % i for i in range(3000)]
+    ks = [vocab[i] for i in rng.integers(0, len(vocab), n)]
+    v = rng.random(n)
+    iv = rng.integers(-9, 9, n, dtype=np.int64)
+    aggs = [AggregateFunction("min", col(1)), AggregateFunction("max", col(1)), AggregateFunction("sum", col(2)), AggregateFunction("count", col(1))]
+    exp = O.aggregate([ks, v, iv], [col(0)], aggs)
+    for nb in [1, 4]:
+        got = gpu_agg(ctx, [ks, v, iv], [col(0)], aggs, nbatches=nb)
+        assert len(got) == 5 and len(got[0]) == len(exp[0])
+        go = sorted(range(len(got[0])), key=lambda i: got[0][i])
+        eo = sorted(range(len(exp[0])), key=lambda i: exp[0][i])
+        assert [got[0][i] for i in go] == [exp[0][i] for i in eo]
+        for c in range(1, 5):
+            assert np.array_equal(np.asarray(got[c])[go], np.asarray(exp[c])[eo])
 
 
 def test_groupby_sentinel_and_extreme_keys(ctx):

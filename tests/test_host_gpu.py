@@ -63,6 +63,14 @@ def test_csv_query_group_by_int_min_max(ctx, golden, fmt_f64):
     assert got == sorted(golden["csv_query_group_by_int_min_max"]["expected"].splitlines(True))
 
 
+def test_csv_query_group_by_string_min_max(ctx, golden, fmt_f64):
+    # tests/sql.rs:55-67 verbatim
+    ctx.register_csv("t1", os.path.join(DATA, "aggregate_test_2.csv"), [("a", A.UTF8), ("b", A.FLOAT64)], 1024)
+    rows = result_rows(ctx.sql(golden["csv_query_group_by_string_min_max"]["sql"]))
+    got = sorted('"%s"\t%s\t%s\n' % (a, fmt_f64(b), fmt_f64(c)) for a, b, c in rows)
+    assert got == sorted(golden["csv_query_group_by_string_min_max"]["expected"].splitlines(True))
+
+
 def test_min_max_lat(ctx, golden):
     register_cities(ctx)
     rel = ctx.sql("SELECT MIN(lat), MAX(lat) FROM cities")
