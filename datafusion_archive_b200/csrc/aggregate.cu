@@ -18,7 +18,7 @@ void utf8_hash(dfgpu_ctx* ctx, const DevColumn& src, long long n, unsigned long 
 void gather_utf8_multi(dfgpu_ctx* ctx, const Utf8Source* d_srcs, const unsigned long long* d_idx, long long nsel, DevColumn* out);
 
 constexpr int AG_THREADS = 256;
-constexpr int AG_R = 4;
+constexpr int AG_R = 2;  // rows per thread per tile: 2 measured best on B200 (1.65 vs 1.74 ms at 4, 1.94 at 8: the kernel is bound by scattered L2 reductions, not by loads in flight)
 constexpr int AG_TILE = AG_THREADS * AG_R;
 constexpr int kMaxAggs = 8;
 constexpr int kMaxKeys = 4;
