@@ -608,6 +608,28 @@ struct dfgpu_aggstate {
 
 namespace {
 
+// DFGPU_TRACE=1: print host-side phase timings of the aggregate operator (each phase synchronised)
+struct Trace {
+  bool on;
+  dfgpu_ctx* ctx;
+  double t0;
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  explicit Trace(dfgpu_ctx* c) : on(getenv("DFGPU_TRACE") != nullptr), ctx(c), t0(0) {
+    if (on) { cudaStreamSynchronize(ctx->stream); t0 = now(); }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    const double t = now();
+    fprintf(stderr, "[dfgpu trace] %-28s %8.3f ms\n", what, t - t0);
+    t0 = t;
+  }
+};
+
 long long next_pow2(long long x) {
   long long p = 1;
   while (p < x) p <<= 1;
@@ -786,6 +808,7 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     ctx->use();
     if (batch->nrows >= (1ll << 32)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "batches of 2^32 rows or more");
 
+    Trace tr(ctx);
     AggParams p;
     memset(&p, 0, sizeof(p));
     ProgramBuilder pb(batch);
@@ -897,6 +920,7 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       for (int a = 0; a < st->naggs; a++)
         if (descs[size_t(a)].dtype != st->descs[size_t(a)].dtype) fail(DFGPU_ERR_GENERAL, "aggregate argument types changed between batches");
     }
+    tr.mark("programs + table alloc");
     pb.finish(&p.ps);
     for (int s = 0; s < p.ps.ncols; s++)
       if (!is_numeric(p.ps.cols[s].dtype))
@@ -945,6 +969,7 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     // groups it produces decides the table layout (SoA while the hot sectors fit L2, AoS beyond) before
     // the bulk of the batch is touched.
     unsigned* ovf[2] = {(unsigned*)ctx->alloc(size_t(batch->nrows) * 4), nullptr};
+    tr.mark("overflow list alloc");
     struct Freer {
       dfgpu_ctx* c;
       unsigned** o;
@@ -988,8 +1013,9 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         st->ngroups = (long long)c[0];
         st->sentinel_used = c[2] != 0;
         const long long novf = (long long)c[1];
+        tr.mark(ri == 0 && ranges.size() > 1 ? "scan kernel (prefix)" : "scan kernel");
         if (novf == 0) {
-          if (st->ngroups > st->cap / 2) table_grow(st, st->cap * 4);  // keep the load factor low for the next batch
+          if (st->ngroups > st->cap / 2) { table_grow(st, st->cap * 4); tr.mark("table_grow (load factor)"); }
           break;
         }
         table_grow(st, st->cap * 4);
@@ -1003,7 +1029,8 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       if (sample && ri == 0 && !st->aos && want_aos(st->ngroups * 2, st->naggs)) {
         // the prefix already produced more groups than SoA keeps hot in L2: rebuild as AoS now
         st->aos = true;
-        table_grow(st, std::max(st->cap, next_pow2(st->ngroups * 8)));
+        table_grow(st, std::max(AG_MIN_CAP, next_pow2(st->ngroups * 4)));  // ~2x the estimated groups at load factor <= 0.5, small enough to stay L2-friendly
+        tr.mark("table_grow (SoA -> AoS)");
       }
     }
     if (ukey) {
@@ -1111,6 +1138,7 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     if (st->finished) fail(DFGPU_ERR_GENERAL, "aggregate already finished");  // one-shot (aggregate.rs:616-619)
     dfgpu_ctx* ctx = st->ctx;
     ctx->use();
+    Trace tr(ctx);
     if (!st->typed) {
       // no batch was ever seen: resolve types from the declared output types
       if (st->nkeys > 0) {
@@ -1206,6 +1234,7 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       }
       DF_CUDA(cudaStreamSynchronize(ctx->stream));
     }
+    tr.mark("finish (compact + outputs)");
     st->finished = true;
     *out = res.release();
   });
