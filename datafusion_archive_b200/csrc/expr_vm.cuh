@@ -22,7 +22,7 @@ enum VOp : uint8_t {
 };
 enum RhsMode : uint8_t { RHS_STACK = 0, RHS_IMM = 1, RHS_COL = 2 };
 
-struct DevInsn {   // 16 bytes, lives in kernel parameter (constant) space
+struct __align__(16) DevInsn {   // 16 bytes, lives in kernel parameter (constant) space
   uint8_t op;      // VOp
   uint8_t mode;    // RhsMode for binary ops
   uint8_t mtype;   // machine type of the operands (CAST: of the source)
@@ -152,6 +152,10 @@ struct GlobalRows {
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
   }
+  __device__ __forceinline__ void load_rows(const ProgramSet& ps, int slot, unsigned long long (&out)[R]) const {
+#pragma unroll
+    for (int r = 0; r < R; r++) out[r] = load(ps, slot, r);
+  }
   __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)rows[r]; }
   // bit r = row r of this thread is non-null in column `slot`
   __device__ __forceinline__ unsigned col_valid(const ProgramSet& ps, int slot) const {
@@ -173,6 +177,34 @@ struct StagedTile {
   long long row0;  // global row number of (tile, lrow0)
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return load_elem_generic(stage + col_off[slot], ps.cols[slot].dtype, lrow0 + r * 32);
+  }
+  // all R rows of a staged column: the dtype dispatch is warp-uniform and paid once, not per row
+  __device__ __forceinline__ void load_rows(const ProgramSet& ps, int slot, unsigned long long (&out)[R]) const {
+    const unsigned char* base = stage + col_off[slot];
+    switch (ps.cols[slot].dtype) {
+      case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64: {
+        const unsigned long long* p = (const unsigned long long*)base + lrow0;
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = p[r * 32];
+        break;
+      }
+      case DFGPU_FLOAT32: case DFGPU_UINT32: {
+        const unsigned* p = (const unsigned*)base + lrow0;
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = (unsigned long long)p[r * 32];
+        break;
+      }
+      case DFGPU_INT32: {
+        const int* p = (const int*)base + lrow0;
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = (unsigned long long)(long long)p[r * 32];
+        break;
+      }
+      default:
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = load(ps, slot, r);
+        break;
+    }
   }
   __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)(row0 + r * 32); }
   __device__ __forceinline__ unsigned col_valid(const ProgramSet&, int) const { return (1u << R) - 1u; }  // staged path is null-free
@@ -274,12 +306,14 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
   unsigned badmask = 0;
   const int begin = ps.start[prog], end = ps.start[prog + 1];
   for (int pc = begin; pc < end; ++pc) {
-    const int op = ps.insn[pc].op;
-    const int mode = ps.insn[pc].mode;
-    const int mt = ps.insn[pc].mtype;
-    const int dt = ps.insn[pc].dtype;
-    const int slot = ps.insn[pc].slot;
-    const unsigned long long imm = ps.insn[pc].imm;
+    // one 16-byte constant-bank read per instruction
+    const uint4 raw = *reinterpret_cast<const uint4*>(&ps.insn[pc]);
+    const int op = raw.x & 0xff;
+    const int mode = (raw.x >> 8) & 0xff;
+    const int mt = (raw.x >> 16) & 0xff;
+    const int dt = (raw.x >> 24) & 0xff;
+    const int slot = (int)(short)(raw.y & 0xffff);
+    const unsigned long long imm = ((unsigned long long)raw.w << 32) | raw.z;
     if (op <= V_PUSH_ROWID) {
       // push
 #pragma unroll
@@ -296,11 +330,10 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
 #pragma unroll
         for (int r = 0; r < R; r++) st[0][r] = src.rowid(r);
       } else {
-#pragma unroll
-        for (int r = 0; r < R; r++) st[0][r] = src.load(ps, slot, r);
+        src.load_rows(ps, slot, st[0]);
       }
     } else if (op == V_CAST) {
-      const int src_dt = ps.insn[pc].aux;
+      const int src_dt = (int)(short)(raw.y >> 16);
 #pragma unroll
       for (int r = 0; r < R; r++) st[0][r] = cast_value(st[0][r], mt, src_dt, dt);
       if (NULLS) {
@@ -316,8 +349,7 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
         for (int r = 0; r < R; r++) rhs[r] = imm;
         if (NULLS) vl = vm[0];
       } else if (mode == RHS_COL) {
-#pragma unroll
-        for (int r = 0; r < R; r++) rhs[r] = src.load(ps, slot, r);
+        src.load_rows(ps, slot, rhs);
         if (NULLS) { vl = vm[0]; vr = src.col_valid(ps, slot); }
       } else {
         // pop: rhs = top, lhs = next; shift the stack down by one

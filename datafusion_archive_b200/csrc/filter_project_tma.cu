@@ -414,18 +414,25 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         const bool wide = F64ONLY || fo.kind;
         // warp-local base pointer once (64-bit), then 32-bit running offsets
         unsigned char* o = (unsigned char*)p.out[q] + base * (unsigned long long)(wide ? 8 : dtype_width_dev(odt));
-        unsigned run = 0;
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const bool f = (flags >> k) & 1u;
-          const unsigned m = __ballot_sync(0xffffffffu, f);
-          if (f) {
-            const unsigned idx = run + __popc(m & lt_mask);
-            if (FAST || wide) ((unsigned long long*)o)[idx] = v[k];
-            else store_elem(o, odt, (long long)idx, v[k]);
-          }
-          run += __popc(m);
+        // compacted store; the element-width dispatch is warp-uniform and hoisted out of the row loop
+#define DF_STORE_LOOP(TYPE)                                                        \
+  {                                                                                \
+    unsigned run = 0;                                                              \
+    _Pragma("unroll") for (int k = 0; k < K; k++) {                                \
+      const bool f = (flags >> k) & 1u;                                            \
+      const unsigned m = __ballot_sync(0xffffffffu, f);                            \
+      if (f) ((TYPE*)o)[run + __popc(m & lt_mask)] = (TYPE)v[k];                   \
+      run += __popc(m);                                                            \
+    }                                                                              \
+  }
+        if (FAST || wide) DF_STORE_LOOP(unsigned long long)
+        else switch (dtype_width_dev(odt)) {
+          case 4: DF_STORE_LOOP(unsigned) break;
+          case 2: DF_STORE_LOOP(unsigned short) break;
+          case 1: DF_STORE_LOOP(unsigned char) break;
+          default: DF_STORE_LOOP(unsigned long long) break;
         }
+#undef DF_STORE_LOOP
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(p.single_ring ? &sh.emptyA[s] : &sh.emptyB[s]);
