@@ -329,27 +329,34 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       }
     }
     // fast shapes (see FPParams): straight from the lowered bytecode
+    auto fast_type = [&](int dt) {
+      return dt == DFGPU_FLOAT64 || dt == DFGPU_INT64 || dt == DFGPU_UINT64 || dt == DFGPU_FLOAT32 || dt == DFGPU_INT32 || dt == DFGPU_UINT32;
+    };
     auto fast_of = [&](int prog, bool is_pred) {
       FastOp f;
       memset(&f, 0, sizeof(f));
       const int b = p.ps.start[prog], e = p.ps.start[prog + 1];
       const DevInsn* in = &p.ps.insn[b];
-      auto f64col = [&](int slot) { return p.ps.cols[slot].dtype == DFGPU_FLOAT64; };
-      if (in[0].op != V_PUSH_COL || !f64col(in[0].slot)) return f;
-      if (e - b == 1 && !is_pred) {
+      if (in[0].op != V_PUSH_COL) return f;
+      const int dt = p.ps.cols[in[0].slot].dtype;
+      if (e - b == 1 && !is_pred) {  // plain column copy: any fixed width
         f.kind = 1;
         f.a = in[0].slot;
+        f.ty = dt;
         return f;
       }
-      if (e - b != 2 || in[1].mtype != MT_F64 || in[1].mode == RHS_STACK) return f;
+      if (e - b != 2 || in[1].mode == RHS_STACK || !fast_type(dt)) return f;
       const bool cmp = in[1].op >= V_EQ && in[1].op <= V_GE, arith = in[1].op >= V_ADD && in[1].op <= V_DIV;
       if (is_pred ? !cmp : !arith) return f;
-      if (in[1].mode == RHS_COL && !f64col(in[1].slot)) return f;
+      if (arith && (dt == DFGPU_INT32 || dt == DFGPU_UINT32)) return f;               // narrow wrap-around: interpreter
+      if (arith && in[1].op == V_DIV && !(dt == DFGPU_FLOAT64 || dt == DFGPU_FLOAT32)) return f;  // integer division: interpreter
+      if (in[1].mode == RHS_COL && p.ps.cols[in[1].slot].dtype != dt) return f;
       f.kind = in[1].mode == RHS_COL ? 2 : 3;
       f.op = in[1].op;
       f.a = in[0].slot;
       f.b = in[1].slot;
-      memcpy(&f.imm, &in[1].imm, 8);
+      f.ty = dt;
+      f.imm = in[1].imm;
       return f;
     };
     memset(&p.pred_fast, 0, sizeof(p.pred_fast));
@@ -360,15 +367,16 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       auto term_at = [&](int i, FastOp* out) {
         if (i + 1 >= e - b) return false;
         const DevInsn &c = in[i], &o = in[i + 1];
-        if (c.op != V_PUSH_COL || p.ps.cols[c.slot].dtype != DFGPU_FLOAT64) return false;
-        if (o.op < V_EQ || o.op > V_GE || o.mtype != MT_F64 || o.mode == RHS_STACK) return false;
-        if (o.mode == RHS_COL && p.ps.cols[o.slot].dtype != DFGPU_FLOAT64) return false;
+        if (c.op != V_PUSH_COL || !fast_type(p.ps.cols[c.slot].dtype)) return false;
+        if (o.op < V_EQ || o.op > V_GE || o.mode == RHS_STACK) return false;
+        if (o.mode == RHS_COL && p.ps.cols[o.slot].dtype != p.ps.cols[c.slot].dtype) return false;
         memset(out, 0, sizeof(*out));
         out->kind = o.mode == RHS_COL ? 2 : 3;
         out->op = o.op;
         out->a = c.slot;
         out->b = o.slot;
-        memcpy(&out->imm, &o.imm, 8);
+        out->ty = p.ps.cols[c.slot].dtype;
+        out->imm = o.imm;
         return true;
       };
       FastPred fp;

@@ -16,7 +16,9 @@ struct FastOp {
   int kind;  // 0 = use the interpreter, 1 = copy column a, 2 = a op column b, 3 = a op imm
   int op;    // VOp
   int a, b;  // column slots
-  double imm;
+  int ty;    // operand dtype: Float64 / Int64 / UInt64 / Float32 / Int32 / UInt32
+  int _pad;
+  unsigned long long imm;  // raw bits, widened like DevInsn::imm
 };
 
 // predicate fast shape: up to 4 Float64 comparisons chained left to right with AND / OR
@@ -51,7 +53,7 @@ struct FPParams {
   int nstagesA, nstagesB;
   int lag;  // tiles between the predicate pass and the projection pass
   int single_ring;  // 1: one ring holds the union of the columns; the projection pass reads the SAME staged tile
-  // "fast shapes": single-operation Float64 programs are recognised on the host and executed by
+  // "fast shapes": single-operation programs over 4- and 8-byte numeric columns are recognised on the host and executed by
   // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).
   //   predicate : chain of (COL cmp COL | COL cmp IMM) joined by AND / OR
   //   projection: COL | COL op COL | COL op IMM          (op in + - * /)

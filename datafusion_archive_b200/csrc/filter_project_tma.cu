@@ -143,13 +143,12 @@ __device__ __forceinline__ void producer_loop(const FPParams& p, int tile_rows, 
   }
 }
 
-// one Float64 comparison over the K rows of this lane -> K flag bits
-template <int K>
-__device__ __forceinline__ unsigned cmp_term(const FastOp& t, const unsigned char* stage, const int* col_off, int lrow0) {
-  const double* A = (const double*)(stage + col_off[t.a]) + lrow0;
+// one comparison over the K rows of this lane -> K flag bits (operands straight from the staged tile)
+template <int K, class T>
+__device__ __forceinline__ unsigned cmp_term_t(const FastOp& t, const unsigned char* stage, const int* col_off, int lrow0, T imm) {
+  const T* A = (const T*)(stage + col_off[t.a]) + lrow0;
   const bool bcol = t.kind == 2;
-  const double* B = bcol ? (const double*)(stage + col_off[t.b]) + lrow0 : A;
-  const double imm = t.imm;
+  const T* B = bcol ? (const T*)(stage + col_off[t.b]) + lrow0 : A;
   unsigned flags = 0;
 #define DF_CMP(OPR)                                                                                    \
   if (bcol) {                                                                                          \
@@ -168,9 +167,55 @@ __device__ __forceinline__ unsigned cmp_term(const FastOp& t, const unsigned cha
 #undef DF_CMP
   return flags;
 }
+template <int K, bool F64>
+__device__ __forceinline__ unsigned cmp_term(const FastOp& t, const unsigned char* stage, const int* col_off, int lrow0) {
+  if (F64) return cmp_term_t<K, double>(t, stage, col_off, lrow0, u2d(t.imm));
+  switch (t.ty) {
+    case DFGPU_FLOAT64: return cmp_term_t<K, double>(t, stage, col_off, lrow0, u2d(t.imm));
+    case DFGPU_INT64: return cmp_term_t<K, long long>(t, stage, col_off, lrow0, (long long)t.imm);
+    case DFGPU_UINT64: return cmp_term_t<K, unsigned long long>(t, stage, col_off, lrow0, t.imm);
+    case DFGPU_FLOAT32: return cmp_term_t<K, float>(t, stage, col_off, lrow0, u2f(t.imm));
+    case DFGPU_INT32: return cmp_term_t<K, int>(t, stage, col_off, lrow0, (int)(long long)t.imm);
+    default: return cmp_term_t<K, unsigned>(t, stage, col_off, lrow0, (unsigned)t.imm);
+  }
+}
+
+// one arithmetic operation over the K rows of this lane (Float64 / Float32 / 64-bit integers)
+template <int K, class T>
+__device__ __forceinline__ void arith_term_t(const FastOp& t, const unsigned char* stage, const int* col_off, int lrow0, T imm, unsigned flags,
+                                             bool& bad, T (&out)[K]) {
+  const T* A = (const T*)(stage + col_off[t.a]) + lrow0;
+  const bool bcol = t.kind == 2;
+  const T* B = bcol ? (const T*)(stage + col_off[t.b]) + lrow0 : A;
+  T y[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) y[k] = bcol ? B[k * 32] : imm;
+  switch (t.op) {
+    case V_ADD:
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = A[k * 32] + y[k];
+      break;
+    case V_SUB:
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = A[k * 32] - y[k];
+      break;
+    case V_MUL:
+#pragma unroll
+      for (int k = 0; k < K; k++) out[k] = A[k * 32] * y[k];
+      break;
+    default:  // V_DIV: floating point only (the host does not select integer division as a fast shape)
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (y[k] == T(0) && ((flags >> k) & 1u)) bad = true;  // DivideByZero on a surviving row
+        out[k] = A[k * 32] / y[k];
+      }
+      break;
+  }
+}
 
 // FAST: every program of the query is a fast shape, so the interpreter is not even compiled into
-// this instantiation (fewer registers, smaller code).
+// this instantiation (fewer registers, smaller code).  FAST + F64ONLY: additionally every operand is
+// Float64, and the per-type dispatch of the fast shapes disappears too (the C2 / C3 kernels).
 template <int DEPTH, int K, bool F64ONLY, bool FAST>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -322,9 +367,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       unsigned flags;
       if (FAST || p.pred_fast.nterms > 0) {
         // fast shape: Float64 comparisons straight from the staged tile, joined by AND / OR
-        flags = cmp_term<K>(p.pred_fast.term[0], src.stage, p.col_offA, src.lrow0);
+        flags = cmp_term<K, FAST && F64ONLY>(p.pred_fast.term[0], src.stage, p.col_offA, src.lrow0);
         for (int t = 1; t < p.pred_fast.nterms; t++) {
-          const unsigned ft = cmp_term<K>(p.pred_fast.term[t], src.stage, p.col_offA, src.lrow0);
+          const unsigned ft = cmp_term<K, FAST && F64ONLY>(p.pred_fast.term[t], src.stage, p.col_offA, src.lrow0);
           flags = p.pred_fast.conn[t] ? (flags | ft) : (flags & ft);
         }
       } else if constexpr (!FAST) {
@@ -374,44 +419,43 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         unsigned long long v[K];
         const FastOp& fo = p.proj_fast[q];
         if (fo.kind == 1 || (FAST && fo.kind < 2)) {
-          const unsigned long long* A = (const unsigned long long*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
+          if (FAST && F64ONLY) {
+            const unsigned long long* A = (const unsigned long long*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
 #pragma unroll
-          for (int k = 0; k < K; k++) v[k] = A[k * 32];
+            for (int k = 0; k < K; k++) v[k] = A[k * 32];
+          } else {
+            src.load_rows(p.ps, fo.a, v);
+          }
         } else if (fo.kind >= 2) {
-          const double* A = (const double*)(src.stage + p.col_offB[fo.a]) + src.lrow0;
-          const bool bcol = fo.kind == 2;
-          const double* B = bcol ? (const double*)(src.stage + p.col_offB[fo.b]) + src.lrow0 : A;
-          const double imm = fo.imm;
-          double y[K];
+          switch ((FAST && F64ONLY) ? (int)DFGPU_FLOAT64 : fo.ty) {
+            case DFGPU_FLOAT64: {
+              double o[K];
+              arith_term_t<K, double>(fo, src.stage, p.col_offB, src.lrow0, u2d(fo.imm), flags, bad, o);
 #pragma unroll
-          for (int k = 0; k < K; k++) y[k] = bcol ? B[k * 32] : imm;
-          switch (fo.op) {
-            case V_ADD:
-#pragma unroll
-              for (int k = 0; k < K; k++) v[k] = d2u(A[k * 32] + y[k]);
+              for (int k = 0; k < K; k++) v[k] = d2u(o[k]);
               break;
-            case V_SUB:
+            }
+            case DFGPU_FLOAT32: {
+              float o[K];
+              arith_term_t<K, float>(fo, src.stage, p.col_offB, src.lrow0, u2f(fo.imm), flags, bad, o);
 #pragma unroll
-              for (int k = 0; k < K; k++) v[k] = d2u(A[k * 32] - y[k]);
+              for (int k = 0; k < K; k++) v[k] = f2u(o[k]);
               break;
-            case V_MUL:
+            }
+            default: {  // Int64 / UInt64: two's complement wrap-around is the natural 64-bit result
+              unsigned long long o[K];
+              arith_term_t<K, unsigned long long>(fo, src.stage, p.col_offB, src.lrow0, fo.imm, flags, bad, o);
 #pragma unroll
-              for (int k = 0; k < K; k++) v[k] = d2u(A[k * 32] * y[k]);
+              for (int k = 0; k < K; k++) v[k] = o[k];
               break;
-            default:
-#pragma unroll
-              for (int k = 0; k < K; k++) {
-                if (y[k] == 0.0 && ((flags >> k) & 1u)) bad = true;  // DivideByZero on a surviving row
-                v[k] = d2u(A[k * 32] / y[k]);
-              }
-              break;
+            }
           }
         } else if constexpr (!FAST) {
           const unsigned b = eval_program<DEPTH, K, F64ONLY>(p.ps, prog, src, v);
           bad = bad || (b != 0);
         }
         const int odt = p.ps.out_dtype[prog];
-        const bool wide = F64ONLY || fo.kind;
+        const bool wide = (FAST && F64ONLY) || dtype_width_dev(odt) == 8;
         // warp-local base pointer once (64-bit), then 32-bit running offsets
         unsigned char* o = (unsigned char*)p.out[q] + base * (unsigned long long)(wide ? 8 : dtype_width_dev(odt));
         // compacted store; the element-width dispatch is warp-uniform and hoisted out of the row loop
@@ -425,7 +469,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       run += __popc(m);                                                            \
     }                                                                              \
   }
-        if (FAST || wide) DF_STORE_LOOP(unsigned long long)
+        if (wide) DF_STORE_LOOP(unsigned long long)
         else switch (dtype_width_dev(odt)) {
           case 4: DF_STORE_LOOP(unsigned) break;
           case 2: DF_STORE_LOOP(unsigned short) break;
@@ -502,7 +546,10 @@ template <int DEPTH, int K>
 static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   bool fast = !p.has_pred || p.pred_fast.nterms > 0;
   for (int q = 0; q < p.nproj; q++) fast = fast && p.proj_fast[q].kind > 0;
-  if (fast) launch_one<1, K, true, true>(ctx, p, smem);
+  bool all_f64 = true;
+  for (int c = 0; c < p.ps.ncols; c++) all_f64 = all_f64 && p.ps.cols[c].dtype == DFGPU_FLOAT64;
+  if (fast && all_f64) launch_one<1, K, true, true>(ctx, p, smem);
+  else if (fast) launch_one<1, K, false, true>(ctx, p, smem);
   else if (p.ps.f64_only) launch_one<DEPTH, K, true, false>(ctx, p, smem);
   else launch_one<DEPTH, K, false, false>(ctx, p, smem);
 }
