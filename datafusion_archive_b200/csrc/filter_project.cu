@@ -304,13 +304,17 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     for (int i = 0; i < nkern; i++) p.out[i] = kern_out[size_t(i)];
     // tile_status is sized for the smallest tile either kernel uses (1024 rows)
     const size_t max_tiles = size_t((n + 1023) / 1024) + 1;
-    unsigned long long* status = (unsigned long long*)ctx->alloc(max_tiles * 8);
-    DF_CUDA(cudaMemsetAsync(status, 0, max_tiles * 8, ctx->stream));
-    DF_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, 32, ctx->stream));
-    p.tile_status = status;
-    p.out_count = ctx->d_scratch + 0;
-    p.ticket = (unsigned*)(ctx->d_scratch + 1);
-    p.err_flag = (unsigned*)(ctx->d_scratch + 2);
+    // one allocation, one memset: [ticket, pad..] then the tile words.  The row count and the error
+    // flag are written by the kernel straight into pinned host memory (zero-copy), so the step ends
+    // with a stream synchronise and no device-to-host copy.
+    unsigned long long* status = (unsigned long long*)ctx->alloc((max_tiles + 8) * 8);
+    DF_CUDA(cudaMemsetAsync(status, 0, (max_tiles + 8) * 8, ctx->stream));
+    ctx->h_scratch[0] = 0;
+    ctx->h_scratch[2] = 0;
+    p.tile_status = status + 8;
+    p.ticket = (unsigned*)(status + 0);
+    p.out_count = ctx->h_scratch + 0;
+    p.err_flag = (unsigned*)(ctx->h_scratch + 2);
     // validity outputs: only a query WITHOUT a predicate can emit nulls (see k_filter_project)
     memset(p.out_valid, 0, sizeof(p.out_valid));
     p.null_counts = ctx->d_scratch + 32;
@@ -407,7 +411,6 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       else if (d <= 4) launch_fp<4>(ctx, p);
       else launch_fp<8>(ctx, p);
     }
-    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch, ctx->d_scratch, 32, cudaMemcpyDeviceToHost, ctx->stream));
     if (p.ps.has_nulls && !has_pred)
       DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 32, ctx->d_scratch + 32, kMaxProgs * 8, cudaMemcpyDeviceToHost, ctx->stream));
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
