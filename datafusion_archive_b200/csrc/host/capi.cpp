@@ -54,6 +54,7 @@ struct dfhost_catalog { std::shared_ptr<Catalog> c = std::make_shared<Catalog>()
 struct dfhost_context { std::unique_ptr<ExecutionContext> ctx; };
 struct dfhost_relation { RelationRef rel; };
 struct dfhost_batch { RecordBatch b; };
+struct dfhost_datasource { DataSourceRef ds; };
 
 extern "C" {
 
@@ -89,6 +90,26 @@ int dfhost_supertype(int32_t l, int32_t r, int32_t* out) {
   return 0;
 }
 int dfhost_debug_f64(double x, char** out) { return guarded([&] { *out = dup_str(rust_debug_f64(x)); }); }
+
+// ---- DataSource on its own (no GPU needed): CsvDataSource::new + next (datasource.rs:33-58) ---------------
+int dfhost_csv_open(const char* filename, int ncols, const char* const* names, const int32_t* dtypes, int64_t batch_size, dfhost_datasource** out) {
+  return guarded([&] {
+    auto d = std::make_unique<dfhost_datasource>();
+    d->ds = std::make_shared<CsvDataSource>(filename, make_schema(ncols, names, dtypes), size_t(batch_size));
+    *out = d.release();
+  });
+}
+int dfhost_datasource_next(dfhost_datasource* d, dfhost_batch** out) {
+  return guarded([&] {
+    *out = nullptr;
+    auto b = d->ds->next();
+    if (!b) return;
+    auto hb = std::make_unique<dfhost_batch>();
+    hb->b = std::move(*b);
+    *out = hb.release();
+  });
+}
+void dfhost_datasource_free(dfhost_datasource* d) { delete d; }
 
 // ---- ExecutionContext -----------------------------------------------------------------------------------
 int dfhost_context_new(int device, dfhost_context** out) {

@@ -50,6 +50,9 @@ def lib():
         L.dfhost_plan_sql.argtypes = [vp, cp, C.POINTER(vp)]
         L.dfhost_supertype.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
         L.dfhost_debug_f64.argtypes = [C.c_double, C.POINTER(vp)]
+        L.dfhost_csv_open.argtypes = [cp, C.c_int, C.POINTER(cp), C.POINTER(C.c_int32), C.c_int64, C.POINTER(vp)]
+        L.dfhost_datasource_next.argtypes = [vp, C.POINTER(vp)]
+        L.dfhost_datasource_free.argtypes = [vp]
         L.dfhost_context_new.argtypes = [C.c_int, C.POINTER(vp)]
         L.dfhost_context_free.argtypes = [vp]
         L.dfhost_context_set_verbose.argtypes = [vp, C.c_int]
@@ -142,6 +145,40 @@ def _col_to_py(col, nulls):
     return vals
 
 
+def _batch_to_py(b):
+    try:
+        nrows, ncols = C.c_int64(), C.c_int()
+        lib().dfhost_batch_shape(b, C.byref(nrows), C.byref(ncols))
+        cols = []
+        for i in range(ncols.value):
+            col, nulls = A.Col(), C.c_int64()
+            _check(lib().dfhost_batch_col(b, i, C.byref(col), C.byref(nulls)))
+            cols.append(_col_to_py(col, nulls.value))
+        return cols
+    finally:
+        lib().dfhost_batch_free(b)
+
+
+class CsvDataSource:
+    """CsvDataSource::new(filename, schema, batch_size) (src/execution/datasource.rs:39-43); CPU only."""
+
+    def __init__(self, filename, fields, batch_size=1024):
+        names, dts = _names_dtypes(fields)
+        self.h = C.c_void_p()
+        _check(lib().dfhost_csv_open(filename.encode(), len(fields), names, dts, batch_size, C.byref(self.h)))
+
+    def next(self):
+        b = C.c_void_p()
+        _check(lib().dfhost_datasource_next(self.h, C.byref(b)))
+        return _batch_to_py(b) if b else None
+
+    def __del__(self):
+        try:
+            lib().dfhost_datasource_free(self.h)
+        except Exception:
+            pass
+
+
 class Relation:
     def __init__(self, handle, keepalive):
         self.h, self._keep = handle, keepalive
@@ -162,17 +199,7 @@ class Relation:
         _check(lib().dfhost_relation_next(self.h, C.byref(b)))
         if not b:
             return None
-        try:
-            nrows, ncols = C.c_int64(), C.c_int()
-            lib().dfhost_batch_shape(b, C.byref(nrows), C.byref(ncols))
-            cols = []
-            for i in range(ncols.value):
-                col, nulls = A.Col(), C.c_int64()
-                _check(lib().dfhost_batch_col(b, i, C.byref(col), C.byref(nulls)))
-                cols.append(_col_to_py(col, nulls.value))
-            return cols
-        finally:
-            lib().dfhost_batch_free(b)
+        return _batch_to_py(b)
 
     def collect(self):
         out = []
