@@ -69,6 +69,10 @@ struct AggParams {
   long long max_groups;      // new keys are refused (-> overflow list) beyond this fill
   unsigned long long* counters;  // [0] ngroups [1] overflow count [2] sentinel-key used [3] error
   unsigned* ovf_rows;
+  // front table (FRONT kernels): one table of front_slots per CTA, or — for very few groups — one
+  // private table per warp, so that shared-memory atomics only contend inside a warp
+  int front_slots;     // power of two
+  int front_per_warp;  // 0 / 1
 };
 
 // ---- order-preserving encodings so that MIN/MAX are native u64 atomics -----------------------
@@ -221,10 +225,14 @@ template <int DEPTH, bool FRONT, bool NULLS>
 __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__ AggParams p) {
   extern __shared__ unsigned long long s_front[];  // FRONT: keys[AG_FRONT_SLOTS] then vals[naggs][AG_FRONT_SLOTS]
   __shared__ int s_full;
+  const int FS = p.front_slots;                                            // slots per front table
+  const int ftables = p.front_per_warp ? AG_THREADS / 32 : 1;              // tables per CTA
+  unsigned long long* ftab = s_front + (p.front_per_warp ? (size_t)(threadIdx.x >> 5) * FS * (1 + p.naggs) : 0);
   if (FRONT) {
-    for (int i = threadIdx.x; i < AG_FRONT_SLOTS; i += AG_THREADS) {
-      s_front[i] = EMPTY_KEY;
-      for (int a = 0; a < p.naggs; a++) s_front[(1 + a) * AG_FRONT_SLOTS + i] = agg_identity(p.aggs[a].func);
+    for (int i = threadIdx.x; i < FS * ftables; i += AG_THREADS) {
+      unsigned long long* tb = s_front + (size_t)(i / FS) * FS * (1 + p.naggs);
+      tb[i % FS] = EMPTY_KEY;
+      for (int a = 0; a < p.naggs; a++) tb[(1 + a) * FS + (i % FS)] = agg_identity(p.aggs[a].func);
     }
     __syncthreads();
   }
@@ -263,12 +271,12 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     for (int r = 0; r < AG_R; r++) {
       fslot[r] = -1;
       if (FRONT && rows[r] >= 0 && key[r] != EMPTY_KEY) {
-        unsigned fh = (unsigned)(mix64(key[r]) >> 40) & (AG_FRONT_SLOTS - 1);
+        unsigned fh = (unsigned)(mix64(key[r]) >> 40) & (unsigned)(FS - 1);
         for (int pr = 0; pr < AG_FRONT_PROBES; pr++) {
-          unsigned long long c = s_front[fh];
-          if (c == EMPTY_KEY) c = atomicCAS(&s_front[fh], EMPTY_KEY, key[r]);
+          unsigned long long c = ftab[fh];
+          if (c == EMPTY_KEY) c = atomicCAS(&ftab[fh], EMPTY_KEY, key[r]);
           if (c == key[r] || c == EMPTY_KEY) { fslot[r] = (int)fh; break; }
-          fh = (fh + 1) & (AG_FRONT_SLOTS - 1);
+          fh = (fh + 1) & (unsigned)(FS - 1);
         }
       }
     }
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
         for (int r = 0; r < AG_R; r++) {
           if (NULLS && func == DFGPU_AGG_COUNT && !((av >> r) & 1u)) continue;  // COUNT counts non-null values
           if (FRONT && fslot[r] >= 0) {
-            acc_fold_shared(func, mt, &s_front[(1 + a) * AG_FRONT_SLOTS + fslot[r]], v[r]);
+            acc_fold_shared(func, mt, &ftab[(1 + a) * FS + fslot[r]], v[r]);
             if ((b >> r) & 1u) bad = true;
           } else if (slot[r] >= 0) {
             acc_fold_global(func, mt, p.t.val(slot[r], a), v[r]);
@@ -327,14 +335,16 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     // front table only exists when groups are few)
     __syncthreads();
     unsigned new_groups = 0;
-    for (int i = threadIdx.x; i < AG_FRONT_SLOTS; i += AG_THREADS) {
-      const unsigned long long key = s_front[i];
+    for (int i = threadIdx.x; i < FS * ftables; i += AG_THREADS) {
+      const unsigned long long* tb = s_front + (size_t)(i / FS) * FS * (1 + p.naggs);
+      const int j = i % FS;
+      const unsigned long long key = tb[j];
       if (key == EMPTY_KEY) continue;
       const unsigned long long h = mix64(key) & hmask;
       const long long slot = probe_insert(p.t, p.cap, key, __ldcg(p.t.key((long long)h)), h, false, new_groups);
       if (slot < 0) { p.counters[3] = 2ull; continue; }
       for (int a = 0; a < p.naggs; a++)
-        acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.t.val(slot, a), s_front[(1 + a) * AG_FRONT_SLOTS + i]);
+        acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.t.val(slot, a), tb[(1 + a) * FS + j]);
     }
     if (new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
   }
@@ -1001,6 +1011,10 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         DF_CUDA(cudaMemsetAsync(st->d_counters + 1, 0, 8, ctx->stream));
         const long long n = list ? nlist : p.nrows;
         const bool front = st->use_front && !list;
+        // <= 64 groups: one private 256-slot table per warp (same shared-memory footprint as the
+        // CTA-wide 2048-slot table); otherwise one table per CTA
+        p.front_per_warp = st->ngroups <= 64 ? 1 : 0;
+        p.front_slots = p.front_per_warp ? AG_FRONT_SLOTS / (AG_THREADS / 32) : AG_FRONT_SLOTS;
         if (p.ps.has_nulls) launch_hash_agg_f<8, false, true>(ctx, p, n);
         else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);

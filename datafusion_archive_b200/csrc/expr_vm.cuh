@@ -152,9 +152,27 @@ struct GlobalRows {
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
   }
+  // all R rows of a column: the dtype dispatch is warp-uniform and paid once, not per row
   __device__ __forceinline__ void load_rows(const ProgramSet& ps, int slot, unsigned long long (&out)[R]) const {
+    const void* base = ps.cols[slot].ptr;
+    switch (ps.cols[slot].dtype) {
+      case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64:
 #pragma unroll
-    for (int r = 0; r < R; r++) out[r] = load(ps, slot, r);
+        for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? __ldg((const unsigned long long*)base + rows[r]) : 0ull;
+        break;
+      case DFGPU_FLOAT32: case DFGPU_UINT32:
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? (unsigned long long)__ldg((const unsigned*)base + rows[r]) : 0ull;
+        break;
+      case DFGPU_INT32:
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? (unsigned long long)(long long)__ldg((const int*)base + rows[r]) : 0ull;
+        break;
+      default:
+#pragma unroll
+        for (int r = 0; r < R; r++) out[r] = load(ps, slot, r);
+        break;
+    }
   }
   __device__ __forceinline__ unsigned long long rowid(int r) const { return (unsigned long long)rows[r]; }
   // bit r = row r of this thread is non-null in column `slot`
