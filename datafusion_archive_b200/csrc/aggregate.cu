@@ -424,6 +424,78 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
   if (bad) p.counters[3] = 1ull;
 }
 
+// K4 fast path: every aggregate argument is a plain, null-free Float64 column.  One pass per distinct
+// column with 128-bit loads; SUM / MIN / MAX / COUNT of the column are all cheap enough to be computed
+// together and the requested ones are merged into the accumulators.
+struct ReduceF64Params {
+  const double* col[kMaxAggs];  // distinct argument columns
+  int ncols;
+  long long nrows;
+  int naggs;
+  AggDesc aggs[kMaxAggs];
+  int agg_arg[kMaxAggs];
+  TableLayout t;
+};
+__global__ void __launch_bounds__(256) k_reduce_f64(const __grid_constant__ ReduceF64Params p) {
+  __shared__ unsigned long long s_red[3][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long npairs = p.nrows >> 1;
+  for (int g = 0; g < p.ncols; g++) {
+    const double2* __restrict__ c2 = reinterpret_cast<const double2*>(p.col[g]);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    unsigned long long mn = ~0ull, mx = 0ull;
+    auto fold = [&](double v, double& s) {
+      s += v;
+      if (v == v) {  // MIN / MAX skip NaN (f64::min / f64::max, aggregate.rs:139-140,208-209)
+        const unsigned long long e = ord_enc(d2u(v), MT_F64);
+        mn = e < mn ? e : mn;
+        mx = e > mx ? e : mx;
+      }
+    };
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + tid;
+    for (; i + stride < npairs; i += 2 * stride) {  // two independent 128-bit loads in flight
+      const double2 a = __ldg(&c2[i]), b = __ldg(&c2[i + stride]);
+      fold(a.x, s0); fold(a.y, s1); fold(b.x, s2); fold(b.y, s3);
+    }
+    if (i < npairs) { const double2 a = __ldg(&c2[i]); fold(a.x, s0); fold(a.y, s1); }
+    if ((p.nrows & 1) && blockIdx.x == 0 && tid == 0) fold(p.col[g][p.nrows - 1], s2);
+    unsigned long long sum = d2u((s0 + s1) + (s2 + s3));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum = d2u(u2d(sum) + u2d(__shfl_xor_sync(0xffffffffu, sum, o)));
+      const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    if (lane == 0) { s_red[0][warp] = sum; s_red[1][warp] = mn; s_red[2][warp] = mx; }
+    __syncthreads();
+    if (warp == 0) {
+      sum = lane < 8 ? s_red[0][lane] : 0ull;
+      mn = lane < 8 ? s_red[1][lane] : ~0ull;
+      mx = lane < 8 ? s_red[2][lane] : 0ull;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        sum = d2u(u2d(sum) + u2d(__shfl_xor_sync(0xffffffffu, sum, o)));
+        const unsigned long long a = __shfl_xor_sync(0xffffffffu, mn, o), b = __shfl_xor_sync(0xffffffffu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+      }
+      if (lane == 0) {
+        for (int a = 0; a < p.naggs; a++) {
+          if (p.agg_arg[a] != g) continue;
+          const int f = p.aggs[a].func;
+          if (f == DFGPU_AGG_SUM) atomicAdd((double*)p.t.val(0, a), u2d(sum));
+          else if (f == DFGPU_AGG_MIN) atomicMin(p.t.val(0, a), mn);
+          else if (f == DFGPU_AGG_MAX) atomicMax(p.t.val(0, a), mx);
+          else if (blockIdx.x == 0) atomicAdd(p.t.val(0, a), (unsigned long long)p.nrows);  // COUNT of a null-free column
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // K7: scan the table, emit occupied slots densely.  raw != 0 keeps packed keys / undecoded
 // accumulators (the exchange format of the multi-GPU merge).
 struct CompactParams {
@@ -963,7 +1035,28 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         launch_reduce<8, true>(ctx, p, p.nrows);
       } else {
         for (int a = 0; a < st->naggs; a++) st->nonnull_host[size_t(a)] += batch->nrows;
-        if (d <= 1) launch_reduce<1>(ctx, p, p.nrows);
+        // fast path: every distinct argument is a plain Float64 column
+        bool plain = true;
+        ReduceF64Params rp;
+        memset(&rp, 0, sizeof(rp));
+        for (int g = 0; g < nargs && plain; g++) {
+          const CompiledProgram& cpg = pb.prog(g);
+          plain = cpg.is_plain_column && p.ps.cols[cpg.plain_slot].dtype == DFGPU_FLOAT64 &&
+                  (reinterpret_cast<uintptr_t>(p.ps.cols[cpg.plain_slot].ptr) & 15) == 0;
+          if (plain) rp.col[g] = (const double*)p.ps.cols[cpg.plain_slot].ptr;
+        }
+        if (plain) {
+          rp.ncols = nargs;
+          rp.nrows = p.nrows;
+          rp.naggs = st->naggs;
+          for (int a = 0; a < st->naggs; a++) { rp.aggs[a] = p.aggs[a]; rp.agg_arg[a] = p.agg_arg[a]; }
+          rp.t = st->t;
+          const int ps = ctx->prof_begin();
+          k_reduce_f64<<<grid_for(ctx, p.nrows, 256 * 8, 8), 256, 0, ctx->stream>>>(rp);
+          DF_CUDA(cudaGetLastError());
+          ctx->prof_end(ps);
+          ctx->launches++;
+        } else if (d <= 1) launch_reduce<1>(ctx, p, p.nrows);
         else if (d <= 2) launch_reduce<2>(ctx, p, p.nrows);
         else if (d <= 4) launch_reduce<4>(ctx, p, p.nrows);
         else launch_reduce<8>(ctx, p, p.nrows);
