@@ -724,6 +724,22 @@ int grid_for(dfgpu_ctx* ctx, long long work_items, int per_block, int blocks_per
 // table is built AoS (one sector per group).  B200 L2 = 126 MB, shared with the streaming input.
 constexpr long long AG_SOA_L2_BUDGET = 48ll << 20;
 
+// Cardinality estimate from a prefix sample: `d` distinct keys among the first `s` rows.  Under a
+// uniform model E[d] = G (1 - exp(-s / G)); solved for G by bisection and capped by the rows of the
+// batch.  Skewed keys make this an under-estimate, which the growth path absorbs.
+long long estimate_groups(long long d, long long s, long long total_rows) {
+  if (d <= 0) return 0;
+  if (double(d) >= 0.995 * double(s)) return total_rows;  // (almost) every sampled row was a new group
+  double lo = double(d), hi = 1e13;
+  for (int it = 0; it < 80; it++) {
+    const double g = 0.5 * (lo + hi);
+    const double e = g * -expm1(-double(s) / g);
+    if (e < double(d)) lo = g; else hi = g;
+  }
+  const double g = 0.5 * (lo + hi);
+  return g > double(total_rows) ? total_rows : (long long)g;
+}
+
 bool want_aos(long long groups, int naggs) { return groups * 32 * (1 + naggs) > AG_SOA_L2_BUDGET; }
 
 TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, const std::vector<AggDesc>& descs, long long cap, bool aos) {
@@ -1133,11 +1149,21 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       }
       // few groups so far: later rows of this stream go through the shared-memory front table
       st->use_front = st->ngroups <= AG_FRONT_MAX_GROUPS && st->rows_seen >= (1ll << 20);
-      if (sample && ri == 0 && !st->aos && want_aos(st->ngroups * 2, st->naggs)) {
-        // the prefix already produced more groups than SoA keeps hot in L2: rebuild as AoS now
-        st->aos = true;
-        table_grow(st, std::max(AG_MIN_CAP, next_pow2(st->ngroups * 4)));  // ~2x the estimated groups at load factor <= 0.5, small enough to stay L2-friendly
-        tr.mark("table_grow (SoA -> AoS)");
+      if (sample && ri == 0) {
+        // size (and lay out) the table for the estimated number of groups before the bulk of the batch
+        // is touched: one rebuild of a ~1 Mi-entry table instead of repeated 4x growth + replays
+        size_t free_b = 0, total_b = 0;
+        DF_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        long long est = std::max(estimate_groups(st->ngroups, kPrefix, batch->nrows), st->ngroups);
+        const long long afford = (long long)(free_b / 8) / (32 * (1 + st->naggs));  // slots that fit in 1/8 of free memory
+        long long want_cap = std::max(AG_MIN_CAP, next_pow2(est * 2));
+        while (want_cap > st->cap && want_cap > afford) want_cap >>= 1;
+        const bool to_aos = !st->aos && want_aos(est, st->naggs);
+        if (to_aos || want_cap > st->cap) {
+          st->aos = st->aos || to_aos;
+          table_grow(st, std::max(st->cap, want_cap));
+          tr.mark("table_grow (prefix estimate)");
+        }
       }
     }
     if (ukey) {

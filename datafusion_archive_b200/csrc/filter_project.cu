@@ -173,6 +173,21 @@ __global__ void __launch_bounds__(FP_THREADS) k_filter_project(const __grid_cons
   }
 }
 
+// one byte per row -> BooleanArray bits (LSB first); one warp packs 32 rows into one word
+__global__ void __launch_bounds__(256) k_pack_bits(const unsigned char* __restrict__ bytes, long long n, unsigned* __restrict__ words) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long padded = (n + 31) / 32 * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += stride) {
+    const unsigned m = __ballot_sync(0xffffffffu, i < n && bytes[i] != 0);
+    if ((threadIdx.x & 31) == 0) words[i >> 5] = m;
+  }
+}
+static int grid_for_rows(dfgpu_ctx* ctx, long long rows) {
+  long long g = (rows + 255) / 256;
+  const long long cap = (long long)ctx->sm_count * 8;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
 template <int DEPTH, bool NULLS = false>
 static void launch_fp(dfgpu_ctx* ctx, const FPParams& p) {
   int per_sm = 0;
@@ -240,7 +255,7 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       }
       int pi = pb.add(proj[i], proj_len[i], "projection");
       int dt = pb.out_dtype(pi);
-      if (!is_numeric(dt))
+      if (!is_numeric(dt) && dt != DFGPU_BOOL)
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("filter/projection output of type ") + dtype_name(dt) +
                                             " is not supported on the GPU path yet");
       out_kind.push_back(nkern++);
@@ -258,10 +273,17 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("expressions over ") + dtype_name(p.ps.cols[s].dtype) + " columns are not supported on the GPU path yet");
     }
     if (p.ps.max_depth > 8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression too deep (register stack depth > 8)");
+    // Boolean projections (comparisons / AND / OR, expression.rs:212-224,236-290) leave the kernel as one
+    // byte per selected row and are bit-packed (BooleanArray layout) once the row count is known.
+    for (int k = 0; k < nkern; k++)
+      if (p.ps.out_dtype[k + has_pred] == DFGPU_BOOL) p.ps.out_dtype[k + has_pred] = DFGPU_UINT8;
 
     auto res = std::make_unique<dfgpu_result>();
     res->ctx = ctx;
     const long long n = batch->nrows;
+    dfgpu_result bool_bytes;  // RAII for the unpacked Boolean outputs
+    bool_bytes.ctx = ctx;
+    std::vector<int> bool_of_out(size_t(nproj), -1);
     // kernel outputs (worst case n rows each); the row-number column is scratch, not a result column
     dfgpu_result scratch;  // RAII for the row-number buffer
     scratch.ctx = ctx;
@@ -270,9 +292,21 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       DevColumn c;
       if (out_kind[size_t(i)] >= 0) {
         c.dtype = pb.out_dtype(out_kind[size_t(i)] + has_pred);
-        c.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(c.dtype));
-        c.values = ctx->alloc(c.values_bytes);
-        kern_out[size_t(out_kind[size_t(i)])] = c.values;
+        if (c.dtype == DFGPU_BOOL) {
+          DevColumn b;
+          b.dtype = DFGPU_UINT8;
+          b.values_bytes = size_t(n > 0 ? n : 1);
+          b.values = ctx->alloc(b.values_bytes);
+          bool_of_out[size_t(i)] = int(bool_bytes.cols.size());
+          bool_bytes.cols.push_back(b);
+          kern_out[size_t(out_kind[size_t(i)])] = b.values;
+          c.values_bytes = size_t((n + 31) / 32) * 4 + 4;  // packed, whole 32-bit words
+          c.values = ctx->alloc(c.values_bytes);
+        } else {
+          c.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(c.dtype));
+          c.values = ctx->alloc(c.values_bytes);
+          kern_out[size_t(out_kind[size_t(i)])] = c.values;
+        }
       } else {
         c.dtype = DFGPU_UTF8;  // filled by the gather below
       }
@@ -287,6 +321,8 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
       kern_out[size_t(rowid_slot)] = c.values;
     }
     if (n == 0) {
+      for (auto& c : res->cols)
+        if (c.dtype == DFGPU_BOOL) c.values_bytes = 0;
       for (auto& c : res->cols)
         if (c.dtype == DFGPU_UTF8) {
           c.offsets = (int32_t*)ctx->alloc(4);
@@ -427,6 +463,19 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     }
     if ((unsigned)ctx->h_scratch[2] != 0) fail(DFGPU_ERR_ARROW, "DivideByZero");
     res->nrows = has_pred ? (int64_t)ctx->h_scratch[0] : n;
+    for (int i = 0; i < nproj; i++)
+      if (bool_of_out[size_t(i)] >= 0) {
+        DevColumn& c = res->cols[size_t(i)];
+        const long long words = (res->nrows + 31) / 32;
+        if (words > 0) {
+          k_pack_bits<<<grid_for_rows(ctx, words * 32), 256, 0, ctx->stream>>>(
+              (const unsigned char*)bool_bytes.cols[size_t(bool_of_out[size_t(i)])].values, res->nrows, (unsigned*)c.values);
+          DF_CUDA(cudaGetLastError());
+          ctx->launches++;
+        }
+        c.values_bytes = size_t(res->nrows + 7) / 8;
+        any_utf8 = true;  // synchronise before the byte buffers are released
+      }
     for (int i = 0; i < nproj; i++)
       if (out_kind[size_t(i)] < 0)
         gather_utf8(ctx, batch->cols[size_t(-1 - out_kind[size_t(i)])], (const unsigned long long*)scratch.cols[0].values, res->nrows,
@@ -584,6 +633,7 @@ extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, 
         for (int q = 0; q < nproj; q++) {
           DevColumn hcol;
           hcol.dtype = ch.res->cols[size_t(q)].dtype;
+          if (!is_numeric(hcol.dtype)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "dfgpu_filter_project_host returns fixed-width numeric columns only");
           hcol.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(hcol.dtype));
           hcol.values = ctx->host_alloc(hcol.values_bytes);
           res->cols.push_back(hcol);

@@ -346,6 +346,7 @@ std::optional<RecordBatch> GpuFilterProjectRelation::next() {
   // zero-copy (the pinned block lives as long as the RecordBatch).
   bool numeric_only = batch->num_rows >= (4ll << 20);
   for (size_t c : pr.cols) numeric_only = numeric_only && datatype_width(batch->columns[c]->data_type) > 0 && batch->columns[c]->null_count == 0;
+  for (auto& f : schema_->fields) numeric_only = numeric_only && datatype_width(f.data_type) > 0;  // Boolean / Utf8 outputs: resident path
   if (numeric_only) {
     std::vector<dfgpu_col> cols;
     for (size_t c : pr.cols) cols.push_back(batch->columns[c]->view());

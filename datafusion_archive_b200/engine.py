@@ -172,6 +172,10 @@ def _fetch_result(L, handle):
             check(L.dfgpu_result_copy_col(handle, i, data.ctypes.data, vptr, offs.ctypes.data))
             raw = data.tobytes()
             vals = [raw[offs[k]:offs[k + 1]].decode() for k in range(n)]
+        elif dt.value == A.BOOL:  # bit-packed, LSB first
+            packed = np.zeros(max(1, (n + 7) // 8), dtype=np.uint8)
+            check(L.dfgpu_result_copy_col(handle, i, packed.ctypes.data, vptr, None))
+            vals = np.unpackbits(packed, bitorder="little")[:n].astype(bool)
         else:
             vals = np.zeros(max(1, n), dtype=A.NP_OF[dt.value])
             check(L.dfgpu_result_copy_col(handle, i, vals.ctypes.data, vptr, None))

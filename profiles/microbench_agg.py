@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Kernel-time microbenchmark of the aggregate operator (CUDA events around k_hash_agg / k_reduce)."""
+"""Kernel-time microbenchmark of the aggregate operator (CUDA events around k_hash_agg / k_reduce).
+usage: microbench_agg.py [rows] [groups,groups,...]   (DFGPU_TRACE=1 prints host-side phase timings)"""
 import os
 import sys
 
@@ -12,7 +13,8 @@ from datafusion_archive_b200.expr import AggregateFunction, col  # noqa: E402
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
 ctx = engine.GpuContext(0)
 v = np.random.default_rng(47).random(n)
-for nkeys in [10, 1000, 100_000, 1_000_000, 10_000_000]:
+group_counts = [int(float(x)) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [10, 1000, 100_000, 1_000_000, 10_000_000]
+for nkeys in group_counts:
     k = workloads.mix_keys(np.random.default_rng(46).integers(0, nkeys, n, dtype=np.int64))
     b = ctx.upload([k, v])
     for name, aggs in [("sum,count", [AggregateFunction("sum", col(1)), AggregateFunction("count", col(1))]),

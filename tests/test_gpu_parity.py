@@ -199,6 +199,25 @@ def test_projection_without_filter(ctx):
     assert_cols_bit_equal(got, exp)
 
 
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 100_003])
+def test_boolean_projection_outputs(ctx, n):
+    # ProjectRelation evaluates any expression (projection.rs:50-58); a comparison or AND / OR yields a
+    # bit-packed BooleanArray (expression.rs:212-224,236-290)
+    rng = np.random.default_rng(5)
+    a, b = rng.random(n), rng.random(n)
+    i = rng.integers(-5, 5, n, dtype=np.int64)
+    arrays = [a, b, i]
+    proj = [col(0) < col(1), (col(0) > lit(0.5)) & (col(2) >= lit(0)), col(0), (col(2).eq(lit(0))) | (col(1) <= lit(0.1)), col(0) + col(1)]
+    if n == 0:
+        got = gpu_fp(ctx, arrays, None, proj)
+        assert [g.dtype for g in got] == [np.dtype(bool), np.dtype(bool), np.dtype("f8"), np.dtype(bool), np.dtype("f8")]
+        assert all(len(g) == 0 for g in got)
+        return
+    assert_cols_bit_equal(gpu_fp(ctx, arrays, None, proj), O.filter_project(arrays, None, proj))
+    pred = col(1) > lit(0.3)
+    assert_cols_bit_equal(gpu_fp(ctx, arrays[:2], pred, proj[:1] + [col(1) >= col(0)]), O.filter_project(arrays[:2], pred, proj[:1] + [col(1) >= col(0)]))
+
+
 def test_compound_predicates_and_nested_expressions(ctx):
     rng = np.random.default_rng(3)
     a, b, c = rng.random(200_000), rng.random(200_000), rng.random(200_000) + 0.5
@@ -548,8 +567,10 @@ def test_nulls_filter_and_projection(ctx):
             assert_nullable_equal(gpu_fp(ctx, arrays, pred, proj), O.filter_project(arrays, pred, proj))
         # no predicate: projections keep / produce nulls
         proj = [col(0), col(0) + col(1), col(0) * lit(2.0), col(2) - col(2), col(0) < col(1), col(3), col(2).cast(A.INT32)]
-        proj_num = [p for p in proj if p is not proj[4]]  # Boolean outputs are not on the GPU path
-        assert_nullable_equal(gpu_fp(ctx, arrays, None, proj_num), O.filter_project(arrays, None, proj_num))
+        assert_nullable_equal(gpu_fp(ctx, arrays, None, proj), O.filter_project(arrays, None, proj))
+        # AND / OR of comparisons over nullable inputs: comparisons are never null, so neither is the result
+        proj = [(col(0) < col(1)) & (col(2) > lit(0)), (col(0) > lit(0.5)) | (col(1) > lit(0.5)), col(0)]
+        assert_nullable_equal(gpu_fp(ctx, arrays, None, proj), O.filter_project(arrays, None, proj))
     finally:
         O.set_extensions(filter_all_primitives=False)
 
