@@ -169,7 +169,9 @@ int dfgpu_batch_free(dfgpu_batch* b);
 /* ---- FilterRelation + ProjectRelation fused (src/execution/filter.rs:46-110,
  *      src/execution/projection.rs:46-66, wiring at src/execution/context.rs:126-161) ----
  * pred_len == 0: no WHERE clause.  nproj == 0: emit every input column (what FilterRelation alone
- * does: filter.rs:55-57).  Output rows keep input order (filter.rs:86-90). */
+ * does: filter.rs:55-57).  Output rows keep input order (filter.rs:86-90).  A projection whose type is
+ * Boolean (a comparison or AND / OR: expression.rs:212-224,236-290) comes back as a DFGPU_BOOL column,
+ * bit-packed LSB first like arrow's BooleanArray; dfgpu_result_col_bytes reports (nrows + 7) / 8. */
 int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_insn* pred, int pred_len,
                          const dfgpu_insn* const* proj, const int* proj_len, int nproj, dfgpu_result** out);
 
