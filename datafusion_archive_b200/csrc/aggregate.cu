@@ -834,13 +834,8 @@ template <int DEPTH, bool FRONT, bool NULLS = false>
 void launch_hash_agg_f(dfgpu_ctx* ctx, const AggParams& p, long long n) {
   const size_t smem = FRONT ? size_t(AG_FRONT_SLOTS) * 8 * size_t(1 + p.naggs) : 0;
   auto kern = k_hash_agg<DEPTH, FRONT, NULLS>;
-  if (FRONT) {
-    static bool configured = false;
-    if (!configured) {
-      DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_FRONT_SLOTS * 8 * (1 + kMaxAggs)));
-      configured = true;
-    }
-  }
+  if (FRONT && ctx->first_use((const void*)kern))
+    DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_FRONT_SLOTS * 8 * (1 + kMaxAggs)));
   int per_sm = 0;
   DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AG_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
@@ -1046,7 +1041,6 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       p.t = st->t;
       p.cap = 0;
       if (p.ps.has_nulls) {
-        if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "nullable inputs with a multi-GPU communicator");
         st->saw_nulls = true;
         launch_reduce<8, true>(ctx, p, p.nrows);
       } else {
@@ -1199,7 +1193,7 @@ void agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st);
 int agg_naggs(const dfgpu_aggstate* st) { return st->naggs; }
 // api.cu (NCCL)
 void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
-                       unsigned long long* d_vals);
+                       unsigned long long* d_vals, unsigned long long* d_nonnull);
 }  // namespace dfgpu
 
 void dfgpu::agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
@@ -1208,7 +1202,20 @@ void dfgpu::agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
     funcs[a] = st->descs[size_t(a)].func;
     mtypes[a] = st->descs[size_t(a)].mtype;
   }
-  agg_exchange_impl(ctx, st, &st->rows_seen, st->nkeys, funcs, mtypes, st->t.val(0, 0));  // no GROUP BY: slot 0's accumulators (cap = 0, SoA: contiguous)
+  if (st->nkeys == 0) {
+    // per-aggregate non-null input counts travel with the accumulators: fold the host-side counts of the
+    // null-free batches into the device counters, which the exchange sums over ranks
+    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 40, st->d_counters + 8, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int a = 0; a < kMaxAggs; a++) {
+      if (a < st->naggs) ctx->h_scratch[40 + a] += (unsigned long long)st->nonnull_host[size_t(a)];
+      if (a < st->naggs) st->nonnull_host[size_t(a)] = 0;
+    }
+    DF_CUDA(cudaMemcpyAsync(st->d_counters + 8, ctx->h_scratch + 40, 64, cudaMemcpyHostToDevice, ctx->stream));
+    st->saw_nulls = true;
+  }
+  agg_exchange_impl(ctx, st, &st->rows_seen, st->nkeys, funcs, mtypes, st->t.val(0, 0),  // no GROUP BY: slot 0's accumulators (cap = 0, SoA: contiguous)
+                    st->d_counters + 8);
 }
 
 void dfgpu::agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n) {
@@ -1357,7 +1364,6 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
         DF_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int a = 0; a < st->naggs; a++) nonnull[size_t(a)] += (long long)ctx->h_scratch[40 + a];
       }
-      if (ctx->world > 1) for (int a = 0; a < st->naggs; a++) nonnull[size_t(a)] = st->rows_seen;  // rows_seen was all-reduced
       for (int a = 0; a < st->naggs; a++) {
         if (nonnull[size_t(a)] > 0 || (st->rows_seen > 0 && st->descs[size_t(a)].func == DFGPU_AGG_COUNT)) continue;
         DevColumn& c = res->cols[size_t(a)];

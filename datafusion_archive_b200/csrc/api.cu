@@ -579,11 +579,11 @@ void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long
 void agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n, long long val_stride);
 int agg_naggs(const dfgpu_aggstate* st);
 void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
-                       unsigned long long* d_vals);
+                       unsigned long long* d_vals, unsigned long long* d_nonnull);
 }  // namespace dfgpu
 
 void dfgpu::agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs,
-                              const int* mtypes, unsigned long long* d_vals) {
+                              const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull) {
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
   if (!comm) fail(DFGPU_ERR_GENERAL, "world > 1 but no communicator");
   const int W = ctx->world, naggs = agg_naggs(st);
@@ -619,6 +619,8 @@ void dfgpu::agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* row
       // f32 accumulators occupy the low 4 bytes of their 8-byte cell
       DF_NCCL(N.AllReduce(d_vals + a, d_vals + a, 1, dt, op, comm, ctx->stream));
     }
+    // non-null input counts per aggregate (an aggregate that saw none anywhere is null)
+    DF_NCCL(N.AllReduce(d_nonnull, d_nonnull, 8, ncclUint64, ncclSum, comm, ctx->stream));
     DF_NCCL(N.GroupEnd());
     DF_CUDA(cudaStreamSynchronize(ctx->stream));
     return;

@@ -96,6 +96,16 @@ struct dfgpu_ctx {
   int rank = 0, world = 1;
   void* nccl_comm = nullptr;
 
+  // kernels whose per-device function attributes (dynamic shared memory limit) were set through this
+  // ctx: the attribute belongs to the device, so it is tracked per ctx and not per process
+  std::vector<const void*> configured_kernels;
+  bool first_use(const void* kernel) {
+    for (const void* k : configured_kernels)
+      if (k == kernel) return false;
+    configured_kernels.push_back(kernel);
+    return true;
+  }
+
   void* alloc(size_t bytes);
   void free(void* p);
   void use();  // cudaSetDevice(device)

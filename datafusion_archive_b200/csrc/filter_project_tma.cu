@@ -527,11 +527,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
 template <int DEPTH, int K, bool F64ONLY, bool FAST>
 static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  if (ctx->first_use((const void*)kern))
     DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 16384 + TM_HDR_BYTES));
-    configured = true;
-  }
   long long grid = std::min(ctx->sm_count, TM_MAX_GRID);  // one persistent CTA per SM
   if (grid > p.ntiles) grid = p.ntiles;
   const int ps = ctx->prof_begin();

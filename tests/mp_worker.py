@@ -62,6 +62,29 @@ def main():
         b = ctx.upload(mine)
         merged = sort_by_key(ctx.aggregate(b, keys, aggs).columns())  # every rank: the GLOBAL result
         smerged = ctx.aggregate(b, [], aggs).columns()
+        # nullable no-GROUP-BY inputs: the non-null counts are summed over ranks, so an aggregate is null
+        # only when NO rank saw a non-null input (array_from_scalar!, aggregate.rs:641-643)
+        import pyarrow as pa
+        lo, hi = parallel.row_range(rank, world, n)
+        v = arrays[1]
+        valid_some = np.zeros(n, dtype=bool)
+        valid_some[: n // (2 * world)] = np.arange(n // (2 * world)) % 3 != 0  # non-null values on rank 0 only
+        valid_none = np.zeros(n, dtype=bool)
+
+        def nullable(values, valid):
+            bits = np.packbits(valid, bitorder="little")
+            return pa.Array.from_buffers(pa.float64(), len(values), [pa.py_buffer(bits.tobytes()), pa.py_buffer(np.ascontiguousarray(values).tobytes())])
+        naggs = [AggregateFunction("min", col(0)), AggregateFunction("sum", col(0)), AggregateFunction("count", col(0)),
+                 AggregateFunction("max", col(1)), AggregateFunction("count", col(1))]
+        nb = ctx.upload([nullable(v[lo:hi], valid_some[lo:hi]), nullable(v[lo:hi], valid_none[lo:hi])])
+        got = ctx.aggregate(nb, [], naggs).columns()
+        exp = O.aggregate([nullable(v, valid_some), nullable(v, valid_none)], [], naggs)
+        unp = lambda c: c if isinstance(c, tuple) else (c, np.ones(len(c), dtype=bool))  # noqa: E731
+        for j, (g, e) in enumerate(zip(got, exp)):
+            (gv, gm), (ev, em) = unp(g), unp(e)
+            assert np.array_equal(gm, em), "validity of aggregate %d differs: %r vs %r" % (j, gm, em)
+            if em[0]:
+                assert gv[0] == ev[0] or abs(gv[0] - ev[0]) <= 1e-9 * abs(ev[0]), (j, gv, ev)
         fb = ctx.upload(fmine)
         fpart = ctx.filter_project(fb, fpred, fproj).columns()
         fg = [None] * world
