@@ -73,6 +73,7 @@ struct AggParams {
   // private table per warp, so that shared-memory atomics only contend inside a warp
   int front_slots;     // power of two
   int front_per_warp;  // 0 / 1
+  int stream_hint;     // 1: input columns are loaded with an L2 evict-first policy
 };
 
 // ---- order-preserving encodings so that MIN/MAX are native u64 atomics -----------------------
@@ -239,6 +240,8 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
   const int tid = threadIdx.x, lane = tid & 31;
   const long long n = p.row_list ? p.nlist : p.nrows;
   const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  // the input is read exactly once: mark its lines evict-first so that they do not displace the table
+  const unsigned long long stream_policy = p.stream_hint ? l2_evict_first_policy() : 0ull;
   bool bad = false;
   for (long long tb = (long long)blockIdx.x * AG_TILE; tb < n; tb += (long long)gridDim.x * AG_TILE) {
     if (tid == 0) s_full = (long long)__ldcg(&p.counters[0]) >= p.max_groups;
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     const bool full = s_full != 0;
     GlobalRows<AG_R> src;
     src.valid = 0;
+    src.l2_policy = stream_policy;
     long long (&rows)[AG_R] = src.rows;
 #pragma unroll
     for (int r = 0; r < AG_R; r++) {
@@ -1118,6 +1122,10 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         // CTA-wide 2048-slot table); otherwise one table per CTA
         p.front_per_warp = st->ngroups <= 64 ? 1 : 0;
         p.front_slots = p.front_per_warp ? AG_FRONT_SLOTS / (AG_THREADS / 32) : AG_FRONT_SLOTS;
+        {
+          static const bool no_hint = getenv("DFGPU_AGG_STREAM_HINT") && atoi(getenv("DFGPU_AGG_STREAM_HINT")) == 0;  // A/B switch
+          p.stream_hint = no_hint ? 0 : 1;
+        }
         if (p.ps.has_nulls) launch_hash_agg_f<8, false, true>(ctx, p, n);
         else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
@@ -1146,10 +1154,8 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       if (sample && ri == 0) {
         // size (and lay out) the table for the estimated number of groups before the bulk of the batch
         // is touched: one rebuild of a ~1 Mi-entry table instead of repeated 4x growth + replays
-        size_t free_b = 0, total_b = 0;
-        DF_CUDA(cudaMemGetInfo(&free_b, &total_b));
         long long est = std::max(estimate_groups(st->ngroups, kPrefix, batch->nrows), st->ngroups);
-        const long long afford = (long long)(free_b / 8) / (32 * (1 + st->naggs));  // slots that fit in 1/8 of free memory
+        const long long afford = (long long)(ctx->device_mem_bytes / 8) / (32 * (1 + st->naggs));  // slots that fit in 1/8 of device memory
         long long want_cap = std::max(AG_MIN_CAP, next_pow2(est * 2));
         while (want_cap > st->cap && want_cap > afford) want_cap >>= 1;
         const bool to_aos = !st->aos && want_aos(est, st->naggs);

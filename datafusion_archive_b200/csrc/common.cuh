@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/dfgpu.h"
@@ -62,6 +64,7 @@ inline bool is_numeric(int dt) { return dt >= DFGPU_INT8 && dt <= DFGPU_FLOAT64;
 struct dfgpu_ctx {
   int device = 0;
   int sm_count = 148;
+  size_t device_mem_bytes = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   int64_t launches = 0;
@@ -106,6 +109,12 @@ struct dfgpu_ctx {
     return true;
   }
 
+  // device memory: see api.cu
+  static constexpr size_t kBigBlock = 256u << 10;
+  std::map<size_t, std::vector<void*>> big_free;  // size class -> cached blocks
+  std::unordered_map<void*, size_t> big_live;     // block -> size class
+  size_t big_cached_bytes = 0;
+  void release_cached();
   void* alloc(size_t bytes);
   void free(void* p);
   void use();  // cudaSetDevice(device)

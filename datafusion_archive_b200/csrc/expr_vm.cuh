@@ -145,10 +145,29 @@ __device__ __forceinline__ unsigned long long load_elem_generic(const void* p, i
 // Operand sources for the evaluator.  GlobalRows: R arbitrary row indices straight from HBM
 // (-1 = past the end).  StagedTile: rows lrow0 + r*32 of a tile staged in shared memory, columns
 // laid out back to back at col_off[slot]; validity comes from `valid` (bit r).
+// 64-bit read-only load with an L2 eviction policy (createpolicy.fractional.L2::evict_first for
+// columns that are streamed exactly once)
+__device__ __forceinline__ unsigned long long ld_stream_u64(const unsigned long long* p, unsigned long long policy) {
+  unsigned long long v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
 template <int R>
 struct GlobalRows {
   long long rows[R];
   unsigned valid;
+  unsigned long long l2_policy = 0;  // createpolicy word for the 64-bit column loads; 0 = default caching
   __device__ __forceinline__ unsigned long long load(const ProgramSet& ps, int slot, int r) const {
     return rows[r] >= 0 ? load_elem(ps.cols[slot].ptr, ps.cols[slot].dtype, rows[r]) : 0ull;
   }
@@ -157,8 +176,13 @@ struct GlobalRows {
     const void* base = ps.cols[slot].ptr;
     switch (ps.cols[slot].dtype) {
       case DFGPU_FLOAT64: case DFGPU_INT64: case DFGPU_UINT64:
+        if (l2_policy) {  // streamed once: do not let the input push a hash table out of L2
 #pragma unroll
-        for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? __ldg((const unsigned long long*)base + rows[r]) : 0ull;
+          for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? ld_stream_u64((const unsigned long long*)base + rows[r], l2_policy) : 0ull;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) out[r] = rows[r] >= 0 ? __ldg((const unsigned long long*)base + rows[r]) : 0ull;
+        }
         break;
       case DFGPU_FLOAT32: case DFGPU_UINT32:
 #pragma unroll
