@@ -75,8 +75,27 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.nvml, self.samples, self.running = None, [], False
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip().isdigit()]
+        return int(ids[self.gpu]) if self.gpu < len(ids) else self.gpu
 
     def start(self):
+        # NVML in a thread (one sample every ~2 ms: the timed region of the resident steps is only a few
+        # ms long); nvidia-smi -lms 100 as the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+            self.nvml = pynvml
+            self.running = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -85,11 +104,39 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        N = self.nvml
+        while self.running:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)
+                try:
+                    rs = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = N.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            N = self.nvml
+            self.running = False
+            self.t.join(timeout=1)
+            try:
+                mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+            reasons = sorted({nm for _, rs, _ in self.samples for nm, b in bits.items() if rs & b})
+            sm = [x[0] for x in self.samples]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w_max": max([x[2] for x in self.samples], default=None),
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, ~2 ms period, warm-up + timed steps"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -112,7 +159,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def dist_setup(n_gpus):

@@ -19,6 +19,15 @@ if which in ("c2", "c3"):
         r = ctx.filter_project(b, pred, proj)
         print(which, "rows out", r.nrows)
         r.free()
+elif which == "reduce":
+    from datafusion_archive_b200.expr import AggregateFunction, col
+    import numpy as np
+    b = ctx.upload([np.random.default_rng(47).random(n)])
+    aggs = [AggregateFunction(f, col(0)) for f in ("min", "max", "sum", "count")]
+    for _ in range(reps):
+        r = ctx.aggregate(b, [], aggs)
+        print(which, "rows", r.nrows)
+        r.free()
 else:
     arrays, keys, aggs, _ = (workloads.c4 if which == "c4" else workloads.c5)(n)
     b = ctx.upload(arrays)
