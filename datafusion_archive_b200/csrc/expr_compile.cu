@@ -227,6 +227,18 @@ int ProgramBuilder::add(const dfgpu_insn* p, int n, const char* what) {
           } else {
             go(nd->r.get());
             di.mode = RHS_STACK;
+            // The evaluator keeps the TOP of the stack (here: the right operand) in its accumulator and
+            // pops the operand below it as the second input, so a stack-mode instruction is emitted with
+            // its operands exchanged: reverse subtract / divide, mirrored comparisons.
+            switch (di.op) {
+              case V_SUB: di.op = V_RSUB; break;
+              case V_DIV: di.op = V_RDIV; break;
+              case V_LT: di.op = V_GT; break;
+              case V_LE: di.op = V_GE; break;
+              case V_GT: di.op = V_LT; break;
+              case V_GE: di.op = V_LE; break;
+              default: break;
+            }
             bump(-1);
           }
           cp->code.push_back(di);

@@ -18,7 +18,8 @@ enum VOp : uint8_t {
   V_PUSH_COL = 0, V_PUSH_IMM, V_PUSH_ROWID /* global row number (gather index of variable-width columns) */, V_CAST,
   V_ADD, V_SUB, V_MUL, V_DIV,
   V_EQ, V_NE, V_LT, V_LE, V_GT, V_GE,
-  V_AND, V_OR
+  V_AND, V_OR,
+  V_RSUB, V_RDIV  // operands exchanged (emitted for stack-mode instructions only, see expr_compile.cu)
 };
 enum RhsMode : uint8_t { RHS_STACK = 0, RHS_IMM = 1, RHS_COL = 2 };
 
@@ -336,15 +337,19 @@ __device__ __forceinline__ unsigned long long cast_value(unsigned long long v, i
 template <int DEPTH, int R, bool F64ONLY, bool NULLS, class Src>
 __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int prog, const Src& src,
                                                    unsigned long long (&out)[R], unsigned& out_valid) {
+  // Accumulator machine: the top of the operand stack lives in `out` (registers, statically indexed);
+  // deeper entries are spilled to a small per-thread array indexed by the run-time depth (local memory,
+  // L1 resident).  A push therefore costs R stores instead of shifting the whole register stack, and a
+  // stack-mode instruction R loads (its operands were exchanged at lowering so that the accumulator is
+  // always the left input).
   constexpr unsigned ALL = (1u << R) - 1u;
-  unsigned vm[DEPTH];
+  constexpr int SPILL = DEPTH > 1 ? DEPTH - 1 : 1;
+  unsigned long long spill[SPILL][R];
+  unsigned spillv[SPILL];
+  unsigned accv = ALL;
+  int depth = 0;
 #pragma unroll
-  for (int d = 0; d < DEPTH; d++) vm[d] = ALL;
-  unsigned long long st[DEPTH][R];
-#pragma unroll
-  for (int d = 0; d < DEPTH; d++)
-#pragma unroll
-    for (int r = 0; r < R; r++) st[d][r] = 0;
+  for (int r = 0; r < R; r++) out[r] = 0;
   unsigned badmask = 0;
   const int begin = ps.start[prog], end = ps.start[prog + 1];
   for (int pc = begin; pc < end; ++pc) {
@@ -357,67 +362,65 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
     const int slot = (int)(short)(raw.y & 0xffff);
     const unsigned long long imm = ((unsigned long long)raw.w << 32) | raw.z;
     if (op <= V_PUSH_ROWID) {
-      // push
+      if (DEPTH > 1 && depth > 0) {  // spill the current top
+        const int d = depth - 1 < SPILL ? depth - 1 : SPILL - 1;
 #pragma unroll
-      for (int d = DEPTH - 1; d > 0; d--) {
-        if (NULLS) vm[d] = vm[d - 1];
-#pragma unroll
-        for (int r = 0; r < R; r++) st[d][r] = st[d - 1][r];
+        for (int r = 0; r < R; r++) spill[d][r] = out[r];
+        if (NULLS) spillv[d] = accv;
       }
-      if (NULLS) vm[0] = op == V_PUSH_COL ? src.col_valid(ps, slot) : ALL;
+      depth++;
+      if (NULLS) accv = op == V_PUSH_COL ? src.col_valid(ps, slot) : ALL;
       if (op == V_PUSH_IMM) {
 #pragma unroll
-        for (int r = 0; r < R; r++) st[0][r] = imm;
+        for (int r = 0; r < R; r++) out[r] = imm;
       } else if (op == V_PUSH_ROWID) {
 #pragma unroll
-        for (int r = 0; r < R; r++) st[0][r] = src.rowid(r);
+        for (int r = 0; r < R; r++) out[r] = src.rowid(r);
       } else {
-        src.load_rows(ps, slot, st[0]);
+        src.load_rows(ps, slot, out);
       }
     } else if (op == V_CAST) {
       const int src_dt = (int)(short)(raw.y >> 16);
 #pragma unroll
-      for (int r = 0; r < R; r++) st[0][r] = cast_value(st[0][r], mt, src_dt, dt);
+      for (int r = 0; r < R; r++) out[r] = cast_value(out[r], mt, src_dt, dt);
       if (NULLS) {
 #pragma unroll
         for (int r = 0; r < R; r++)
-          if (!((vm[0] >> r) & 1u)) st[0][r] = 0ull;
+          if (!((accv >> r) & 1u)) out[r] = 0ull;
       }
     } else {
-      unsigned long long rhs[R];
-      unsigned vr = ALL, vl = ALL;
+      unsigned long long y[R];
+      unsigned vb = ALL;
+      const unsigned va = accv;
       if (mode == RHS_IMM) {
 #pragma unroll
-        for (int r = 0; r < R; r++) rhs[r] = imm;
-        if (NULLS) vl = vm[0];
+        for (int r = 0; r < R; r++) y[r] = imm;
       } else if (mode == RHS_COL) {
-        src.load_rows(ps, slot, rhs);
-        if (NULLS) { vl = vm[0]; vr = src.col_valid(ps, slot); }
+        src.load_rows(ps, slot, y);
+        if (NULLS) vb = src.col_valid(ps, slot);
       } else {
-        // pop: rhs = top, lhs = next; shift the stack down by one
+        // pop the entry below the top (the instruction's left operand before the exchange)
+        depth--;
+        const int d = depth - 1 >= 0 ? (depth - 1 < SPILL ? depth - 1 : SPILL - 1) : 0;
 #pragma unroll
-        for (int r = 0; r < R; r++) rhs[r] = st[0][r];
-        if (NULLS) { vr = vm[0]; vl = vm[DEPTH > 1 ? 1 : 0]; }
-#pragma unroll
-        for (int d = 0; d < DEPTH - 1; d++) {
-          if (NULLS) vm[d] = vm[d + 1];
-#pragma unroll
-          for (int r = 0; r < R; r++) st[d][r] = st[d + 1][r];
-        }
+        for (int r = 0; r < R; r++) y[r] = spill[d][r];
+        if (NULLS) vb = spillv[d];
       }
-      const unsigned both = vl & vr;
+      const unsigned both = va & vb;
       // The (machine type, op) dispatch is hoisted out of the per-row loop: it is warp-uniform and
       // paid once per R rows.  A zero divisor sets the row's bit in badmask (arrow 0.12
       // array_ops::divide returns ArrowError::DivideByZero for ints and floats alike).
-#define DF_ROWS(EXPR) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long a = st[0][r], b = rhs[r]; (void)a; (void)b; st[0][r] = (EXPR); }
-#define DF_DIVCHK(COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long b = rhs[r]; if ((COND) && (!NULLS || ((both >> r) & 1u))) badmask |= 1u << r; }
-      switch (F64ONLY ? (op >= V_AND ? (int)MT_BOOL : (int)MT_F64) : mt) {
+#define DF_ROWS(EXPR) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long a = out[r], b = y[r]; (void)a; (void)b; out[r] = (EXPR); }
+#define DF_DIVCHK(WHICH, COND) _Pragma("unroll") for (int r = 0; r < R; r++) { const unsigned long long z = WHICH[r]; if ((COND) && (!NULLS || ((both >> r) & 1u))) badmask |= 1u << r; }
+      switch (F64ONLY ? (op == V_AND || op == V_OR ? (int)MT_BOOL : (int)MT_F64) : mt) {
         case MT_F64:
           switch (op) {
             case V_ADD: DF_ROWS(d2u(u2d(a) + u2d(b))) break;
             case V_SUB: DF_ROWS(d2u(u2d(a) - u2d(b))) break;
+            case V_RSUB: DF_ROWS(d2u(u2d(b) - u2d(a))) break;
             case V_MUL: DF_ROWS(d2u(u2d(a) * u2d(b))) break;
-            case V_DIV: DF_DIVCHK(u2d(b) == 0.0) DF_ROWS(d2u(u2d(a) / u2d(b))) break;
+            case V_DIV: DF_DIVCHK(y, u2d(z) == 0.0) DF_ROWS(d2u(u2d(a) / u2d(b))) break;
+            case V_RDIV: DF_DIVCHK(out, u2d(z) == 0.0) DF_ROWS(d2u(u2d(b) / u2d(a))) break;
             case V_EQ: DF_ROWS((unsigned long long)(u2d(a) == u2d(b))) break;
             case V_NE: DF_ROWS((unsigned long long)(u2d(a) != u2d(b))) break;
             case V_LT: DF_ROWS((unsigned long long)(u2d(a) < u2d(b))) break;
@@ -430,8 +433,10 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
           switch (op) {
             case V_ADD: DF_ROWS(f2u(u2f(a) + u2f(b))) break;
             case V_SUB: DF_ROWS(f2u(u2f(a) - u2f(b))) break;
+            case V_RSUB: DF_ROWS(f2u(u2f(b) - u2f(a))) break;
             case V_MUL: DF_ROWS(f2u(u2f(a) * u2f(b))) break;
-            case V_DIV: DF_DIVCHK(u2f(b) == 0.0f) DF_ROWS(f2u(u2f(a) / u2f(b))) break;
+            case V_DIV: DF_DIVCHK(y, u2f(z) == 0.0f) DF_ROWS(f2u(u2f(a) / u2f(b))) break;
+            case V_RDIV: DF_DIVCHK(out, u2f(z) == 0.0f) DF_ROWS(f2u(u2f(b) / u2f(a))) break;
             case V_EQ: DF_ROWS((unsigned long long)(u2f(a) == u2f(b))) break;
             case V_NE: DF_ROWS((unsigned long long)(u2f(a) != u2f(b))) break;
             case V_LT: DF_ROWS((unsigned long long)(u2f(a) < u2f(b))) break;
@@ -441,14 +446,14 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
           }
           break;
         case MT_I:
+#define DF_SDIV(N, D) ((D) == 0ull ? 0ull : ((long long)(D) == -1ll ? norm_int(0ull - (N), dt) : norm_int((unsigned long long)((long long)(N) / (long long)(D)), dt)))
           switch (op) {
             case V_ADD: DF_ROWS(norm_int(a + b, dt)) break;
             case V_SUB: DF_ROWS(norm_int(a - b, dt)) break;
+            case V_RSUB: DF_ROWS(norm_int(b - a, dt)) break;
             case V_MUL: DF_ROWS(norm_int(a * b, dt)) break;
-            case V_DIV:
-              DF_DIVCHK(b == 0ull)
-              DF_ROWS(b == 0ull ? 0ull : ((long long)b == -1ll ? norm_int(0ull - a, dt) : norm_int((unsigned long long)((long long)a / (long long)b), dt)))
-              break;
+            case V_DIV: DF_DIVCHK(y, z == 0ull) DF_ROWS(DF_SDIV(a, b)) break;
+            case V_RDIV: DF_DIVCHK(out, z == 0ull) DF_ROWS(DF_SDIV(b, a)) break;
             case V_EQ: DF_ROWS((unsigned long long)(a == b)) break;
             case V_NE: DF_ROWS((unsigned long long)(a != b)) break;
             case V_LT: DF_ROWS((unsigned long long)((long long)a < (long long)b)) break;
@@ -456,13 +461,16 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
             case V_GT: DF_ROWS((unsigned long long)((long long)a > (long long)b)) break;
             default: DF_ROWS((unsigned long long)((long long)a >= (long long)b)) break;
           }
+#undef DF_SDIV
           break;
         case MT_U:
           switch (op) {
             case V_ADD: DF_ROWS(norm_int(a + b, dt)) break;
             case V_SUB: DF_ROWS(norm_int(a - b, dt)) break;
+            case V_RSUB: DF_ROWS(norm_int(b - a, dt)) break;
             case V_MUL: DF_ROWS(norm_int(a * b, dt)) break;
-            case V_DIV: DF_DIVCHK(b == 0ull) DF_ROWS(b == 0ull ? 0ull : a / b) break;
+            case V_DIV: DF_DIVCHK(y, z == 0ull) DF_ROWS(b == 0ull ? 0ull : a / b) break;
+            case V_RDIV: DF_DIVCHK(out, z == 0ull) DF_ROWS(a == 0ull ? 0ull : b / a) break;
             case V_EQ: DF_ROWS((unsigned long long)(a == b)) break;
             case V_NE: DF_ROWS((unsigned long long)(a != b)) break;
             case V_LT: DF_ROWS((unsigned long long)(a < b)) break;
@@ -484,11 +492,12 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
 #undef DF_DIVCHK
       if (NULLS) {
         if (op >= V_EQ && op <= V_GE) {
-          // comparisons: never null; a null operand is ordered, not propagated
+          // comparisons: never null; a null operand is ordered, not propagated (a = accumulator = the
+          // left input of the instruction as emitted, b = y = its right input)
 #pragma unroll
           for (int r = 0; r < R; r++) {
             if (!((both >> r) & 1u)) {
-              const bool ln = !((vl >> r) & 1u), rn = !((vr >> r) & 1u);
+              const bool ln = !((va >> r) & 1u), rn = !((vb >> r) & 1u);
               bool v;
               switch (op) {
                 case V_EQ: v = ln && rn; break;
@@ -496,23 +505,21 @@ __device__ __forceinline__ unsigned eval_program_n(const ProgramSet& ps, int pro
                 case V_LT: case V_LE: v = ln; break;
                 default: v = rn; break;
               }
-              st[0][r] = v ? 1ull : 0ull;
+              out[r] = v ? 1ull : 0ull;
             }
           }
-          vm[0] = ALL;
+          accv = ALL;
         } else {
           // arithmetic, And, Or: null if either side is null; append_null stores the default value
 #pragma unroll
           for (int r = 0; r < R; r++)
-            if (!((both >> r) & 1u)) st[0][r] = 0ull;
-          vm[0] = both;
+            if (!((both >> r) & 1u)) out[r] = 0ull;
+          accv = both;
         }
       }
     }
   }
-#pragma unroll
-  for (int r = 0; r < R; r++) out[r] = st[0][r];
-  out_valid = NULLS ? vm[0] : ALL;
+  out_valid = NULLS ? accv : ALL;
   return badmask & src.valid;
 }
 

@@ -19,6 +19,18 @@ if which in ("c2", "c3"):
         r = ctx.filter_project(b, pred, proj)
         print(which, "rows out", r.nrows)
         r.free()
+elif which == "deep":
+    from datafusion_archive_b200.expr import col, lit
+    import numpy as np
+    b = ctx.upload([np.random.default_rng(1).random(n)])
+    pred = (col(0) * col(0)) < lit(0.3)
+    proj = [(col(0) + col(0)) * (col(0) - lit(1.0)) / (col(0) + lit(2.0))]
+    ctx.profile_enable(True)
+    for _ in range(reps):
+        r = ctx.filter_project(b, pred, proj)
+        r.free()
+    ms, k = ctx.profile_get()
+    print(which, "kernel ms", ms / k)
 elif which == "reduce":
     from datafusion_archive_b200.expr import AggregateFunction, col
     import numpy as np
