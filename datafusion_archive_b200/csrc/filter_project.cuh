@@ -52,6 +52,7 @@ struct FPParams {
   int stage_bytesA, stage_bytesB;
   int nstagesA, nstagesB;
   int lag;  // tiles between the predicate pass and the projection pass
+  int count_ballot; // 1: per-tile counts via K ballots (A/B switch); 0: one REDUX per warp
   int single_ring;  // 1: one ring holds the union of the columns; the projection pass reads the SAME staged tile
   // "fast shapes": single-operation programs over 4- and 8-byte numeric columns are recognised on the host and executed by
   // straight-line code instead of the interpreter (same arithmetic, no decode in the inner loop).

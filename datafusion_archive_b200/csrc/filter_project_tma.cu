@@ -385,10 +385,15 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         for (int k = 0; k < K; k++) flags |= (unsigned)(v[k] & 1ull) << k;
       }
       flags &= src.valid;
+      // rows this warp selected in the tile: one population count per lane, one warp reduction (REDUX)
       unsigned cnt = 0;
+      if (p.count_ballot) {  // A/B switch (DFGPU_FP_COUNT=ballot): the pre-REDUX form
 #pragma unroll
-      for (int k = 0; k < K; k++) cnt += __popc(__ballot_sync(0xffffffffu, (flags >> k) & 1u));
-      __syncwarp();
+        for (int k = 0; k < K; k++) cnt += __popc(__ballot_sync(0xffffffffu, (flags >> k) & 1u));
+        __syncwarp();
+      } else {
+        cnt = __reduce_add_sync(0xffffffffu, (unsigned)__popc(flags));
+      }
       if (lane == 0) {
         if (!p.single_ring) mbar_arrive(&sh.emptyA[s]);  // this warp is done reading the stage
         sh.s_cnt[it % TM_RING][warp] = cnt;
@@ -659,6 +664,10 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
     }
   }
   p.ntiles = int((p.nrows + tile - 1) / tile);
+  {
+    const char* e = getenv("DFGPU_FP_COUNT");
+    p.count_ballot = (e && std::string(e) == "ballot") ? 1 : 0;
+  }
   const size_t smem = TM_HDR_BYTES + (size_t)p.nstagesA * p.stage_bytesA + (size_t)p.nstagesB * p.stage_bytesB;
   const int d = p.ps.max_depth;
   if (K == 8) launch_k<2, 8>(ctx, p, smem);
