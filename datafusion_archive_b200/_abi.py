@@ -1,7 +1,7 @@
 """ctypes mirror of include/dfgpu.h (the C ABI of the sm_100a engine).
 
-Only plain-old-data definitions live here so that the test-only oracle wrapper
-(tests/oracle_lib.py) can share them.  Nothing in this module touches a GPU.
+Only plain-old-data definitions live here so that the test-only CPU checker under
+tests/ can share them.  Nothing in this module touches a GPU.
 """
 import ctypes as C
 import os
