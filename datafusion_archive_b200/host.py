@@ -134,6 +134,9 @@ def _col_to_py(col, nulls):
         offs = np.ctypeslib.as_array(C.cast(col.offsets, C.POINTER(C.c_int32)), shape=(col.offset + n + 1,))[col.offset:]
         raw = C.string_at(col.values, int(offs[-1])) if n else b""
         vals = [raw[offs[k]:offs[k + 1]].decode() for k in range(n)]
+    elif col.dtype == A.BOOL:  # bit-packed, LSB first
+        bits = np.frombuffer(C.string_at(col.values, (col.offset + n + 7) // 8), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+        vals = np.unpackbits(bits, bitorder="little")[col.offset:col.offset + n].astype(bool)
     else:
         dt = np.dtype(A.NP_OF[col.dtype])
         buf = C.string_at(col.values + col.offset * dt.itemsize, n * dt.itemsize) if n else b""

@@ -45,3 +45,32 @@ def test_typed_columns_and_errors(golden):
     with pytest.raises(host.ExecutionError) as e:  # a Utf8 field parsed as a number
         drain(host.CsvDataSource(os.path.join(DATA, "uk_cities.csv"), [("city", A.FLOAT64), ("lat", A.FLOAT64), ("lng", A.FLOAT64)], 1024))
     assert "ParseError" in e.value.msg
+
+
+def test_empty_fields_become_nulls_and_boolean_columns():
+    # test/data/null_test.csv of the reference (no reference test reads it: semantics restated from the
+    # arrow 0.12 csv reader — empty primitive field -> null, empty Utf8 field -> "", bool via str::parse)
+    fields = [("c_int", A.INT32), ("c_float", A.FLOAT64), ("c_string", A.UTF8), ("c_bool", A.BOOL)]
+    # has_headers = true: the header line is the one that is dropped here
+    (b,) = drain(host.CsvDataSource(os.path.join(DATA, "null_test.csv"), fields, 1024))
+    assert list(b[0]) == [1, 2, 3, 4, 5]
+    vals, mask = b[1]
+    assert list(mask) == [True, True, False, True, True]
+    assert list(vals[mask]) == [1.1, 2.2, 4.4, 6.6] and vals[2] == 0.0
+    assert b[2] == ["1.11", "2.22", "3.33", "", ""]
+    assert b[3].dtype == bool and list(b[3]) == [True, True, True, False, False]
+    # ragged batches keep validity aligned
+    parts = drain(host.CsvDataSource(os.path.join(DATA, "null_test.csv"), fields, 2))
+    assert [len(p[0]) for p in parts] == [2, 2, 1]
+    assert isinstance(parts[1][1], tuple) and list(parts[1][1][1]) == [False, True]
+    assert not isinstance(parts[0][1], tuple)  # no nulls in the first batch: no bitmap
+
+
+@pytest.mark.parametrize("text,dtype", [("1,abc\n", A.INT32), ("1,300\n", A.INT8), ("1,-1\n", A.UINT16), ("1, 5\n", A.INT64),
+                                        ("1,5x\n", A.FLOAT64), ("1,yes\n", A.BOOL), ("1,99999999999999999999\n", A.INT64)])
+def test_unparsable_values_are_parse_errors(tmp_path, text, dtype):
+    f = tmp_path / "t.csv"
+    f.write_text("a,b\n" + text)
+    with pytest.raises(host.ExecutionError) as e:
+        drain(host.CsvDataSource(str(f), [("a", A.INT32), ("b", dtype)], 16))
+    assert "ParseError" in e.value.msg and "line 2" in e.value.msg
