@@ -64,3 +64,12 @@ def test_aggregates_skip_nulls(ctx):
     assert unpack(got[0])[0][0] == unpack(exp[0])[0][0] == 1.1
     assert unpack(got[1])[0][0] == unpack(exp[1])[0][0] == 6.6
     assert abs(unpack(got[2])[0][0] - unpack(exp[2])[0][0]) <= 1e-9 * abs(unpack(exp[2])[0][0])
+
+
+def test_project_all_columns(ctx):
+    # src/execution/projection.rs:83-103: ProjectRelation over people.csv with [Column(0)] -> one column named "id"
+    ctx.register_csv("people", os.path.join(DATA, "people.csv"), [("id", A.INT32), ("first_name", A.UTF8)], 1024)
+    rel = ctx.sql("SELECT id FROM people")
+    assert rel.schema() == [("id", A.INT32)]
+    (batch,) = rel.collect()
+    assert len(batch) == 1 and batch[0].dtype == np.int32 and batch[0][0] == 1
