@@ -1126,6 +1126,38 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
           static const bool no_hint = getenv("DFGPU_AGG_STREAM_HINT") && atoi(getenv("DFGPU_AGG_STREAM_HINT")) == 0;  // A/B switch
           p.stream_hint = no_hint ? 0 : 1;
         }
+        // Experiment (default off, DFGPU_AGG_L2_PERSIST=1): pin the table in the
+        // persisting part of L2 for the scan, let everything else stream.
+        static const bool l2_persist = getenv("DFGPU_AGG_L2_PERSIST") && atoi(getenv("DFGPU_AGG_L2_PERSIST")) != 0;
+        if (l2_persist) {
+          cudaDeviceProp prop;
+          DF_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+          const size_t tbytes = size_t(st->cap + 1) * 8 * size_t(st->aos ? st->t.sstride : 1 + st->naggs);
+          const size_t window = std::min(tbytes, size_t(prop.accessPolicyMaxWindowSize));
+          const size_t carve = std::min(window, size_t(prop.persistingL2CacheMaxSize));
+          if (carve > 0) {
+            DF_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            av.accessPolicyWindow.base_ptr = st->t.base;
+            av.accessPolicyWindow.num_bytes = window;
+            av.accessPolicyWindow.hitRatio = float(double(carve) / double(window));
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            DF_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
+          }
+        }
+        struct L2Reset {
+          dfgpu_ctx* c;
+          bool on;
+          ~L2Reset() {
+            if (!on) return;
+            cudaStreamAttrValue av;
+            memset(&av, 0, sizeof(av));
+            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+            cudaCtxResetPersistingL2Cache();
+          }
+        } l2_reset{ctx, l2_persist};
         if (p.ps.has_nulls) launch_hash_agg_f<8, false, true>(ctx, p, n);
         else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
