@@ -102,11 +102,24 @@ struct Parser {
     return 0;
   }
 
+  // The parser, the planner and the plan printer recurse over the expression tree: bound its depth and
+  // size so that hostile input ends in a ParserError instead of a stack overflow (the reference's
+  // recursive-descent parser would abort the process).
+  static constexpr int kMaxExprDepth = 400, kMaxExprNodes = 4000;
+  int depth_ = 0, nodes_ = 0;
+
   ASTRef parse_expr(int precedence = 0) {
+    struct Depth {
+      int& d;
+      explicit Depth(int& x) : d(x) { ++d; }
+      ~Depth() { --d; }
+    } guard(depth_);
+    if (depth_ > kMaxExprDepth) perr("expression nested too deeply");
     ASTRef expr = parse_prefix();
     for (;;) {
       int np = next_precedence();
       if (precedence >= np) break;
+      if (++nodes_ > kMaxExprNodes) perr("expression too large");
       expr = parse_infix(expr, np);
     }
     return expr;

@@ -99,3 +99,33 @@ def test_rust_debug_f64(golden):
     assert host.debug_f64(1e16) == "1e16" and host.debug_f64(1e15) == "1000000000000000.0"
     assert host.debug_f64(1.5e-7) == "1.5e-7" and host.debug_f64(0.00001) == "0.00001"
     assert host.debug_f64(-0.0) == "-0.0"
+
+
+def test_hostile_sql_ends_in_parser_errors_not_crashes(mock):
+    # the parser, planner and plan printer recurse over the tree: depth and size are bounded
+    for sql in ["SELECT " + "(" * 100_000 + "age" + ")" * 100_000 + " FROM person",
+                "SELECT " + " + ".join(["age"] * 100_000) + " FROM person",
+                "SELECT " + "CAST(" * 50_000 + "age" + " AS int)" * 50_000 + " FROM person",
+                "SELECT " + "sqrt(" * 50_000 + "age" + ")" * 50_000 + " FROM person"]:
+        with pytest.raises(host.ExecutionError) as e:
+            mock.plan(sql)
+        assert "ParserError" in str(e.value)
+    assert mock.plan("SELECT " + "(" * 300 + "age" + ")" * 300 + " FROM person").startswith("Projection: #3")
+    assert mock.plan("SELECT " + " + ".join(["age"] * 3000) + " FROM person").count("Plus") == 2999
+    # random token soup: every input is either planned or rejected with an error
+    import random
+    rnd = random.Random(7)
+    toks = ["SELECT", "FROM", "WHERE", "GROUP", "BY", "ORDER", "LIMIT", "AND", "OR", "NOT", "AS", "CAST", "(", ")", ",", "*", "+", "-", "/", "%",
+            "=", "<", ">", "<=", ">=", "<>", "!=", "id", "age", "salary", "state", "person", "nobody", "COUNT", "MIN", "sqrt", "1", "2.5", "'x'",
+            "'", "NULL", "IS", "int", "double", ";", "DESC", "1e400", "99999999999999999999", ".", "--", "\\"]
+    planned = 0
+    for _ in range(3000):
+        sql = ("SELECT " if rnd.random() < 0.6 else "") + " ".join(rnd.choice(toks) for _ in range(rnd.randint(1, 12)))
+        if rnd.random() < 0.5:
+            sql += " FROM person"
+        try:
+            mock.plan(sql)
+            planned += 1
+        except host.ExecutionError:
+            pass
+    assert planned > 0
