@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "execution.h"
+#include "../../../include/dfhost.h"  // the declarations this file defines (signature check)
 
 using namespace dfhost;
 

@@ -34,6 +34,17 @@ def test_library_exports_every_declared_symbol():
     assert L.dfgpu_abi_version() == A.ABI_VERSION
 
 
+def test_host_mirror_library_exports_its_header():
+    # include/dfhost.h: the harness API of the C++ host mirror (not the drop-in boundary)
+    from datafusion_archive_b200 import host
+    host.build()
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dfhost.h")).read(), flags=re.S)
+    syms = sorted(set(re.findall(r"\b(dfhost_[a-z0-9_]+)\s*\(", src)))
+    assert len(syms) >= 25
+    L = ctypes.CDLL(os.path.join(ROOT, "datafusion_archive_b200", "libdfhost.so"))
+    assert [s for s in syms if not hasattr(L, s)] == []
+
+
 def test_struct_layout_matches_header():
     # sizes the C side static-asserts implicitly through use; keep the ctypes mirror honest
     assert ctypes.sizeof(A.Insn) == 24
