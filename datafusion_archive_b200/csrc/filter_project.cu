@@ -209,6 +209,25 @@ void gather_utf8(dfgpu_ctx* ctx, const DevColumn& src, const unsigned long long*
 }
 using namespace dfgpu;
 
+// Host-only type check of one expression program (no ctx, no device): the same ProgramBuilder the
+// operators use, over a schema-only stand-in for a batch.
+extern "C" int dfgpu_check_program(const int32_t* col_dtypes, int ncols, const dfgpu_insn* prog, int prog_len, int32_t* out_dtype) {
+  return guarded([&] {
+    if (!col_dtypes || ncols < 0 || !prog || prog_len <= 0 || !out_dtype) fail(DFGPU_ERR_GENERAL, "dfgpu_check_program: null argument");
+    dfgpu_batch schema_only;  // ctx == nullptr: owns nothing, its destructor frees nothing
+    for (int i = 0; i < ncols; i++) {
+      DevColumn c;
+      c.dtype = col_dtypes[i];
+      schema_only.cols.push_back(c);
+    }
+    ProgramBuilder pb(&schema_only);
+    const int pi = pb.add(prog, prog_len, "expression");
+    ProgramSet ps;
+    pb.finish(&ps);  // instruction / column-slot limits
+    *out_dtype = pb.out_dtype(pi);
+  });
+}
+
 extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_insn* pred, int pred_len,
                                     const dfgpu_insn* const* proj, const int* proj_len, int nproj, dfgpu_result** out) {
   return guarded([&] {

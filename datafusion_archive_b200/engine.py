@@ -187,6 +187,19 @@ def _fetch_result(L, handle):
     return cols
 
 
+def check_program(schema_dtypes, expr):
+    """dfgpu_check_program: type-check `expr` against a schema (list of dtype codes) on the host, no GPU.
+    Returns the result dtype; raises DfGpuError exactly as the operators would."""
+    prog = expr.program(list(schema_dtypes))
+    arr = (A.Insn * max(1, len(prog)))(*prog)
+    dts = (C.c_int32 * max(1, len(schema_dtypes)))(*schema_dtypes)
+    out = C.c_int32()
+    L = lib()
+    L.dfgpu_check_program.argtypes = [C.POINTER(C.c_int32), C.c_int, C.POINTER(A.Insn), C.c_int, C.POINTER(C.c_int32)]
+    check(L.dfgpu_check_program(dts, len(schema_dtypes), arr, len(prog), C.byref(out)))
+    return out.value
+
+
 class Batch:
     def __init__(self, ctx, handle, schema):
         self.ctx, self.h, self.schema = ctx, handle, schema

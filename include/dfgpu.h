@@ -166,6 +166,13 @@ int dfgpu_batch_upload(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, dfgpu_b
 int dfgpu_batch_rows(const dfgpu_batch* b, int64_t* nrows);
 int dfgpu_batch_free(dfgpu_batch* b);
 
+/* ---- compile_scalar_expr's checks alone (src/execution/expression.rs:283-505) ----
+ * Type-check one expression program against a schema (`col_dtypes[i]` = dtype of column i) exactly as
+ * dfgpu_filter_project / dfgpu_aggregate_update would before launching anything, without touching a
+ * GPU: identical operand dtypes ("math_ops" / "comparison_ops"), Boolean operands for AND / OR, the CAST
+ * rules, column indices.  `out_dtype` receives the result type.  Usable on a machine with no device. */
+int dfgpu_check_program(const int32_t* col_dtypes, int ncols, const dfgpu_insn* prog, int prog_len, int32_t* out_dtype);
+
 /* ---- FilterRelation + ProjectRelation fused (src/execution/filter.rs:46-110,
  *      src/execution/projection.rs:46-66, wiring at src/execution/context.rs:126-161) ----
  * pred_len == 0: no WHERE clause.  nproj == 0: emit every input column (what FilterRelation alone
