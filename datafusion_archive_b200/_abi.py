@@ -8,7 +8,7 @@ import os
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # error codes
 OK, ERR_GENERAL, ERR_EXECUTION, ERR_NOT_IMPLEMENTED, ERR_INVALID_COLUMN, ERR_INTERNAL, ERR_ARROW, ERR_CUDA, ERR_OOM = range(9)

@@ -33,20 +33,49 @@ struct AggDesc {
   uint8_t out_dtype;
 };
 
-// Table addressing.  Two layouts share one code path:
-//   SoA (sstride = 1, voff = astride = cap+1): keys[cap+1] then one array per aggregate.  A row's probe
-//        and reductions go to different L2 slices in parallel: fastest while the touched sectors of all
-//        arrays fit in L2 (measured: 1e5 groups, 2 aggs: 1.67 ms vs 2.41 ms for AoS).
-//   AoS (sstride = W = pow2 >= 1+naggs, voff = 1, astride = 1): one 32/64-byte slot per group.  One
-//        sector per group instead of 1+naggs: wins once the table no longer fits L2
-//        (measured: 1e6 groups, 3 aggs: 3.17 ms vs 5.28 ms; 1e7 groups: 7.1 ms vs 11.2 ms).
+// Table addressing.  A slot is a LINE of lw 64-bit words (lw a power of two; word 0 = the packed key) plus
+// one word in each of n_add separate arrays.  loc[a] says where accumulator a lives: >= 1 = that word of
+// the line, < 0 = additive array ~loc[a].  Three layouts fall out of it (measured on B200,
+// profiles/r02a_scatter_ops2.txt and profiles/r01m_microbench_agg.txt):
+//   SoA     lw = 1, every accumulator in its own array.  A row's probe and reductions go to different L2
+//           slices in parallel; reductions that hit the SAME 32-byte sector as the probe serialise in the
+//           slice (LDG + 2 RED on one sector: 2.04 ms per 1e8 rows against 1.38 ms on three arrays).
+//   hybrid  MIN / MAX accumulators share the line with the key, SUM / COUNT stay in arrays.  The probe is
+//           one 128/256-bit load that also returns the current MIN / MAX, and a MIN / MAX reduction is only
+//           issued when the row improves on the value just read (monotone accumulators: a stale read can
+//           only cause a redundant reduction, never a missed one).  After a group's first few rows almost
+//           no row does, so MIN + MAX + SUM costs one load and one reduction per row instead of one load
+//           and three reductions.
+//   line    every accumulator in the line (lw >= 1 + naggs): one sector per group; wins once the table no
+//           longer fits L2 and every touched sector is an HBM transaction (1e7 groups: 7.1 vs 11.2 ms).
 struct TableLayout {
-  unsigned long long* base;
-  long long sstride, voff, astride;
-  __host__ __device__ __forceinline__ unsigned long long* key(long long slot) const { return base + slot * sstride; }
+  unsigned long long* base;  // (cap + 1) lines of lw words
+  unsigned long long* add;   // n_add arrays of (cap + 1) words
+  long long lw, astride;
+  signed char loc[kMaxAggs];
+  __host__ __device__ __forceinline__ unsigned long long* key(long long slot) const { return base + slot * lw; }
   __host__ __device__ __forceinline__ unsigned long long* val(long long slot, int a) const {
-    return base + voff + slot * sstride + (long long)a * astride;
+    const int l = loc[a];
+    return l >= 0 ? base + slot * lw + l : add + (long long)(~l) * astride + slot;
   }
+};
+
+// plain-column fast path (k_hash_agg_plain): every key and aggregate argument is a plain column and the
+// WHERE clause, if any, is a chain of column comparisons: no interpreter in the kernel
+struct PlainTerm {
+  int a, b;      // column slots (b: right-hand column when kind == 2)
+  int kind;      // 2 = col cmp col, 3 = col cmp imm
+  int op;        // VOp (V_EQ .. V_GE)
+  int mt;        // machine type of the operands
+  int conn;      // joins the running result with this term: 0 = AND, 1 = OR
+  unsigned long long imm;
+};
+struct PlainSpec {
+  int ncols;                  // distinct column slots referenced (<= 4): ps.cols[0 .. ncols)
+  int key_slot[kMaxKeys];
+  int arg_slot[kMaxAggs];     // per distinct argument program
+  int nterms;                 // predicate terms (0 = no predicate)
+  PlainTerm term[4];
 };
 
 struct AggParams {
@@ -74,6 +103,11 @@ struct AggParams {
   int front_slots;     // power of two
   int front_per_warp;  // 0 / 1
   int stream_hint;     // 1: input columns are loaded with an L2 evict-first policy
+  // fused WHERE (Aggregate{input: Selection}, context.rs:126-139,162-192): program 0 is the predicate and
+  // the key / argument programs follow; rows that fail it are skipped before the probe
+  int has_pred;
+  int cond_mm;         // 1: MIN / MAX reductions are skipped when the value read with the probe already covers the row
+  PlainSpec plain;
 };
 
 // ---- order-preserving encodings so that MIN/MAX are native u64 atomics -----------------------
@@ -172,25 +206,65 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   return x;
 }
 
-// Find the slot of `key`, claiming an empty one when the key is new.  Returns -1 when the key is
-// new and the table refuses new keys (fill limit / probe limit): the row goes to the overflow list.
-__device__ __forceinline__ long long probe_insert(const TableLayout& t, long long cap, unsigned long long key,
-                                                  unsigned long long first_cur, unsigned long long h, bool full,
-                                                  unsigned& new_groups) {
+// One table line as read by a probe: word 0 = key, words 1..3 = the accumulators that share the line.
+struct Line {
+  unsigned long long w[4];
+};
+template <bool WITH_VALS>
+__device__ __forceinline__ void load_line(const TableLayout& t, long long slot, Line& ln) {
+  const unsigned long long* q = t.key(slot);
+  if (WITH_VALS && t.lw >= 4) {  // 256-bit load (LDG.E.ENL2.256): lines are 32-byte aligned
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ln.w[0]), "=l"(ln.w[1]), "=l"(ln.w[2]), "=l"(ln.w[3]) : "l"(q) : "memory");
+  } else if (WITH_VALS && t.lw == 2) {
+    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(ln.w[0]), "=l"(ln.w[1]) : "l"(q) : "memory");
+    ln.w[2] = ln.w[3] = 0ull;
+  } else {
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(ln.w[0]) : "l"(q) : "memory");
+    ln.w[1] = ln.w[2] = ln.w[3] = 0ull;
+  }
+}
+__device__ __forceinline__ unsigned long long line_word(const Line& ln, int l) {
+  return l == 1 ? ln.w[1] : (l == 2 ? ln.w[2] : ln.w[3]);
+}
+
+// Find the slot of `key`, claiming an empty one when the key is new.  `ln` is the line read at the home
+// slot h on entry and the line of the returned slot on exit (as it was when this thread read it: a slot
+// claimed meanwhile still shows its initial accumulator identities, which is what the conditional
+// MIN / MAX update needs).  Returns -1 when the key is new and the table refuses new keys (fill limit /
+// probe limit): the row goes to the overflow list.
+template <bool WITH_VALS>
+__device__ __forceinline__ long long probe_insert(const TableLayout& t, long long cap, unsigned long long key, Line& ln,
+                                                  unsigned long long h, bool full, unsigned& new_groups) {
   const unsigned long long mask = (unsigned long long)cap - 1ull;
-  unsigned long long cur = first_cur;
   for (int probes = 0; probes < AG_MAX_PROBE; ++probes) {
-    if (cur == key) return (long long)h;
-    if (cur == EMPTY_KEY) {
+    if (ln.w[0] == key) return (long long)h;
+    if (ln.w[0] == EMPTY_KEY) {
       if (full) return -1;
       const unsigned long long old = atomicCAS(t.key((long long)h), EMPTY_KEY, key);
       if (old == EMPTY_KEY) { new_groups++; return (long long)h; }
       if (old == key) return (long long)h;
     }
     h = (h + 1ull) & mask;
-    cur = __ldcg(t.key((long long)h));
+    load_line<WITH_VALS>(t, (long long)h, ln);
   }
   return -1;
+}
+
+// fold one raw value into global memory; `cur` = the accumulator as read with the probe (have_cur): a
+// MIN / MAX that the row does not improve needs no reduction (the stored value only moves towards it)
+__device__ __forceinline__ void acc_fold_global_cond(int func, int mt, unsigned long long* p, unsigned long long v, bool have_cur,
+                                                     unsigned long long cur) {
+  if (func == DFGPU_AGG_MIN) {
+    if (is_nan_val(v, mt)) return;
+    const unsigned long long e = ord_enc(v, mt);
+    if (!have_cur || e < cur) atomicMin(p, e);
+  } else if (func == DFGPU_AGG_MAX) {
+    if (is_nan_val(v, mt)) return;
+    const unsigned long long e = ord_enc(v, mt);
+    if (!have_cur || e > cur) atomicMax(p, e);
+  } else {
+    acc_fold_global(func, mt, p, v);
+  }
 }
 
 // fold one raw value into a shared-memory accumulator (front table)
@@ -215,17 +289,159 @@ constexpr int AG_FRONT_SLOTS = 2048;   // per-CTA shared-memory front table (low
 constexpr int AG_FRONT_PROBES = 8;
 constexpr int AG_FRONT_MAX_GROUPS = 1024;
 
+// ---- row sources of the scan kernel -----------------------------------------------------------------
+// InterpSrc: keys, arguments and the WHERE predicate are expression programs run by the interpreter of
+// expr_vm.cuh, AG_R rows per thread.
+// NULLS: like the reference, keys and MIN/MAX/SUM arguments are read ignoring the validity bitmap
+// (`array.value(row)`, aggregate.rs:561-601, 807-852; a null produced by arithmetic reads as the
+// builder's default 0); only COUNT (an extension, §DESIGN) honours nulls.  A predicate that evaluates to
+// null reads as its value false (filter.rs:86 `filter.value(i)`).
+template <int DEPTH, bool NULLS>
+struct InterpSrc {
+  static constexpr int R = AG_R;
+  GlobalRows<R> g;
+  unsigned mask;  // rows to aggregate: in range and passing the predicate
+  unsigned bad = 0;
+  __device__ __forceinline__ InterpSrc(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
+    g.valid = 0;
+    g.l2_policy = policy;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const long long i = tb + (long long)r * AG_THREADS + tid;
+      g.rows[r] = i < n ? (p.row_list ? (long long)p.row_list[i] : p.row_begin + i) : -1;
+      if (i < n) g.valid |= 1u << r;
+    }
+    mask = g.valid;
+    if (p.has_pred) {
+      unsigned long long v[R];
+      unsigned pv;
+      bad |= eval_program_n<DEPTH, R, false, NULLS>(p.ps, 0, g, v, pv);  // FilterRelation evaluates the predicate on every row
+      unsigned keep = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) keep |= (unsigned)(v[r] & 1ull) << r;
+      mask &= keep;
+    }
+  }
+  __device__ __forceinline__ void key(const AggParams& p, int k, unsigned long long (&v)[R]) {
+    unsigned kv;
+    bad |= eval_program_n<DEPTH, R, false, NULLS>(p.ps, p.has_pred + k, g, v, kv) & mask;
+  }
+  // returns the DivideByZero bits of the rows; av = validity bits of the argument values
+  __device__ __forceinline__ unsigned arg(const AggParams& p, int gi, unsigned long long (&v)[R], unsigned& av) {
+    return eval_program_n<DEPTH, R, false, NULLS>(p.ps, p.has_pred + p.nkeys + gi, g, v, av);
+  }
+  __device__ __forceinline__ unsigned rowid(int r) const { return (unsigned)g.rows[r]; }
+};
+
+// PlainSrc: every key / argument is a plain 4- or 8-byte column and the predicate a chain of column
+// comparisons.  A thread owns two CONSECUTIVE rows, so an 8-byte column is one 128-bit load per thread
+// (coalesced 512 bytes per warp instruction) and a 4-byte column one 64-bit load; values are kept in the
+// widened 64-bit machine representation of the interpreter, so everything downstream is shared.
+__device__ __forceinline__ void ld_pair64(const void* base, long long row, bool both, unsigned long long policy, unsigned long long (&out)[2]) {
+  const unsigned long long* q = (const unsigned long long*)base + row;
+  if (both) {
+    if (policy)
+      asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.b64 {%0, %1}, [%2], %3;" : "=l"(out[0]), "=l"(out[1]) : "l"(q), "l"(policy));
+    else
+      asm volatile("ld.global.nc.L1::no_allocate.v2.b64 {%0, %1}, [%2];" : "=l"(out[0]), "=l"(out[1]) : "l"(q));
+  } else {
+    out[0] = __ldg(q);
+    out[1] = 0ull;
+  }
+}
+__device__ __forceinline__ void ld_pair32(const void* base, long long row, bool both, bool sign, unsigned long long (&out)[2]) {
+  const unsigned* q = (const unsigned*)base + row;
+  unsigned lo, hi = 0;
+  if (both) {
+    const uint2 t = __ldg((const uint2*)q);
+    lo = t.x;
+    hi = t.y;
+  } else {
+    lo = __ldg(q);
+  }
+  out[0] = sign ? (unsigned long long)(long long)(int)lo : (unsigned long long)lo;
+  out[1] = sign ? (unsigned long long)(long long)(int)hi : (unsigned long long)hi;
+}
+__device__ __forceinline__ unsigned cmp_bits2(int op, int mt, const unsigned long long (&a)[2], const unsigned long long (&b)[2]) {
+  unsigned f = 0;
+#define DF_C2(EXPR) _Pragma("unroll") for (int r = 0; r < 2; r++) { const unsigned long long x = a[r], y = b[r]; f |= (unsigned)(EXPR) << r; }
+#define DF_C2_OPS(CAST)                           \
+  switch (op) {                                   \
+    case V_EQ: DF_C2(CAST(x) == CAST(y)) break;   \
+    case V_NE: DF_C2(CAST(x) != CAST(y)) break;   \
+    case V_LT: DF_C2(CAST(x) < CAST(y)) break;    \
+    case V_LE: DF_C2(CAST(x) <= CAST(y)) break;   \
+    case V_GT: DF_C2(CAST(x) > CAST(y)) break;    \
+    default: DF_C2(CAST(x) >= CAST(y)) break;     \
+  }
+  switch (mt) {
+    case MT_F64: DF_C2_OPS(u2d) break;
+    case MT_F32: DF_C2_OPS(u2f) break;
+    case MT_I: DF_C2_OPS((long long)) break;
+    default: DF_C2_OPS((unsigned long long)) break;
+  }
+#undef DF_C2_OPS
+#undef DF_C2
+  return f;
+}
+struct PlainSrc {
+  static constexpr int R = 2;
+  unsigned long long cv[4][2];
+  long long row0;
+  unsigned mask;
+  unsigned bad = 0;
+  // value selects instead of indexed access: the column values stay in registers
+  __device__ __forceinline__ void col(int s, unsigned long long (&v)[2]) const {
+    v[0] = s == 0 ? cv[0][0] : (s == 1 ? cv[1][0] : (s == 2 ? cv[2][0] : cv[3][0]));
+    v[1] = s == 0 ? cv[0][1] : (s == 1 ? cv[1][1] : (s == 2 ? cv[2][1] : cv[3][1]));
+  }
+  __device__ __forceinline__ PlainSrc(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
+    const long long i = tb + 2ll * tid;
+    row0 = p.row_begin + i;  // even: tb and row_begin are even (host-checked)
+    mask = (i < n ? 1u : 0u) | (i + 1 < n ? 2u : 0u);
+    const bool both = mask == 3u;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      cv[c][0] = cv[c][1] = 0ull;
+      if (c < p.plain.ncols && mask) {
+        const int dt = p.ps.cols[c].dtype;  // warp-uniform
+        if (dt == DFGPU_FLOAT64 || dt == DFGPU_INT64 || dt == DFGPU_UINT64) ld_pair64(p.ps.cols[c].ptr, row0, both, policy, cv[c]);
+        else ld_pair32(p.ps.cols[c].ptr, row0, both, dt == DFGPU_INT32, cv[c]);
+      }
+    }
+    if (p.plain.nterms > 0) {
+      unsigned keep = 0;
+      for (int t = 0; t < p.plain.nterms; t++) {
+        const PlainTerm& pt = p.plain.term[t];
+        unsigned long long x[2], y[2];
+        col(pt.a, x);
+        if (pt.kind == 2) col(pt.b, y);
+        else y[0] = y[1] = pt.imm;
+        const unsigned f = cmp_bits2(pt.op, pt.mt, x, y);
+        keep = t == 0 ? f : (pt.conn ? (keep | f) : (keep & f));
+      }
+      mask &= keep;
+    }
+  }
+  __device__ __forceinline__ void key(const AggParams& p, int k, unsigned long long (&v)[2]) { col(p.plain.key_slot[k], v); }
+  __device__ __forceinline__ unsigned arg(const AggParams& p, int gi, unsigned long long (&v)[2], unsigned& av) {
+    col(p.plain.arg_slot[gi], v);
+    av = 3u;
+    return 0u;
+  }
+  __device__ __forceinline__ unsigned rowid(int r) const { return (unsigned)(row0 + r); }
+};
+
+// K5 scan.  Per row: key -> mix64 -> linear probing over table lines (ld.global.cg, 64/128/256 bits: the
+// probe also brings the in-line MIN / MAX accumulators) -> atomicCAS to claim an empty slot -> one
+// fire-and-forget L2 reduction per additive accumulator and per MIN / MAX that the row improves.
 // FRONT: a per-CTA open-addressed table in shared memory absorbs the updates (shared-memory atomics),
 // and is merged into the global table once, when the CTA is done.  Used when the sampled prefix shows
 // few groups: with a handful of hot keys every global reduction would serialise on the same L2 sector
 // (measured: 10 groups, 1e8 rows: 21 ms through L2 atomics).
-// NULLS: like the reference, keys and MIN/MAX/SUM arguments are read ignoring the validity bitmap
-// (`array.value(row)`, aggregate.rs:561-601, 807-852; a null produced by arithmetic reads as the
-// builder's default 0); only COUNT (an extension, §DESIGN) honours nulls.
-template <int DEPTH, bool FRONT, bool NULLS>
-__global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__ AggParams p) {
-  extern __shared__ unsigned long long s_front[];  // FRONT: keys[AG_FRONT_SLOTS] then vals[naggs][AG_FRONT_SLOTS]
-  __shared__ int s_full;
+template <class Src, bool FRONT, bool NULLS>
+__device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long long* s_front) {
+  constexpr int R = Src::R;
   const int FS = p.front_slots;                                            // slots per front table
   const int ftables = p.front_per_warp ? AG_THREADS / 32 : 1;              // tables per CTA
   unsigned long long* ftab = s_front + (p.front_per_warp ? (size_t)(threadIdx.x >> 5) * FS * (1 + p.naggs) : 0);
@@ -243,38 +459,30 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
   // the input is read exactly once: mark its lines evict-first so that they do not displace the table
   const unsigned long long stream_policy = p.stream_hint ? l2_evict_first_policy() : 0ull;
   bool bad = false;
-  for (long long tb = (long long)blockIdx.x * AG_TILE; tb < n; tb += (long long)gridDim.x * AG_TILE) {
-    if (tid == 0) s_full = (long long)__ldcg(&p.counters[0]) >= p.max_groups;
-    __syncthreads();
-    const bool full = s_full != 0;
-    GlobalRows<AG_R> src;
-    src.valid = 0;
-    src.l2_policy = stream_policy;
-    long long (&rows)[AG_R] = src.rows;
-#pragma unroll
-    for (int r = 0; r < AG_R; r++) {
-      const long long i = tb + (long long)r * AG_THREADS + tid;
-      rows[r] = i < n ? (p.row_list ? (long long)p.row_list[i] : p.row_begin + i) : -1;
-      if (i < n) src.valid |= 1u << r;
-    }
+  constexpr int TILE = AG_THREADS * R;
+  for (long long tb = (long long)blockIdx.x * TILE; tb < n; tb += (long long)gridDim.x * TILE) {
+    // fill limit, once per warp per tile (no CTA-wide barrier in the steady state)
+    unsigned long long filled = 0;
+    if (lane == 0) filled = __ldcg(&p.counters[0]);
+    filled = __shfl_sync(0xffffffffu, filled, 0);
+    const bool full = (long long)filled >= p.max_groups;
+    Src src(p, tb, n, tid, stream_policy);
     // group key: one packed 64-bit word (GroupByScalar vector of aggregate.rs:807-852)
-    unsigned long long key[AG_R];
+    unsigned long long key[R];
 #pragma unroll
-    for (int r = 0; r < AG_R; r++) key[r] = 0;
+    for (int r = 0; r < R; r++) key[r] = 0;
     for (int k = 0; k < p.nkeys; k++) {
-      unsigned long long v[AG_R];
-      unsigned kv;
-      const unsigned b = eval_program_n<DEPTH, AG_R, false, NULLS>(p.ps, k, src, v, kv);
-      bad = bad || (b != 0);
+      unsigned long long v[R];
+      src.key(p, k, v);
 #pragma unroll
-      for (int r = 0; r < AG_R; r++) key[r] |= (v[r] & p.key_mask[k]) << p.key_shift[k];
+      for (int r = 0; r < R; r++) key[r] |= (v[r] & p.key_mask[k]) << p.key_shift[k];
     }
     // front table (shared memory): claim / find the key there first
-    int fslot[AG_R];
+    int fslot[R];
 #pragma unroll
-    for (int r = 0; r < AG_R; r++) {
+    for (int r = 0; r < R; r++) {
       fslot[r] = -1;
-      if (FRONT && rows[r] >= 0 && key[r] != EMPTY_KEY) {
+      if (FRONT && ((src.mask >> r) & 1u) && key[r] != EMPTY_KEY) {
         unsigned fh = (unsigned)(mix64(key[r]) >> 40) & (unsigned)(FS - 1);
         for (int pr = 0; pr < AG_FRONT_PROBES; pr++) {
           unsigned long long c = ftab[fh];
@@ -285,58 +493,64 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
       }
     }
     // first probe of all R rows issued back to back (R independent L2 requests in flight)
-    unsigned long long h[AG_R], cur[AG_R];
+    unsigned long long h[R];
+    Line ln[R];
+    bool probing[R];
 #pragma unroll
-    for (int r = 0; r < AG_R; r++) {
+    for (int r = 0; r < R; r++) {
       h[r] = mix64(key[r]) & hmask;
-      cur[r] = (rows[r] >= 0 && key[r] != EMPTY_KEY && fslot[r] < 0) ? __ldcg(p.t.key((long long)h[r])) : 0ull;
+      probing[r] = ((src.mask >> r) & 1u) && key[r] != EMPTY_KEY && fslot[r] < 0;
+      ln[r].w[0] = ln[r].w[1] = ln[r].w[2] = ln[r].w[3] = 0ull;
+      if (probing[r]) load_line<true>(p.t, (long long)h[r], ln[r]);
     }
-    long long slot[AG_R];
+    long long slot[R];
     unsigned new_groups = 0;
 #pragma unroll
-    for (int r = 0; r < AG_R; r++) {
-      if (rows[r] < 0 || fslot[r] >= 0) { slot[r] = -1; continue; }
+    for (int r = 0; r < R; r++) {
+      slot[r] = -1;
+      if (!((src.mask >> r) & 1u) || fslot[r] >= 0) continue;
       if (key[r] == EMPTY_KEY) {  // the one key value that collides with the empty marker
         if (__ldcg(&p.counters[2]) == 0ull) p.counters[2] = 1ull;
         slot[r] = p.cap;
         continue;
       }
-      slot[r] = probe_insert(p.t, p.cap, key[r], cur[r], h[r], full, new_groups);
+      slot[r] = probe_insert<true>(p.t, p.cap, key[r], ln[r], h[r], full, new_groups);
       if (slot[r] < 0) {
         const unsigned long long at = atomicAdd(&p.counters[1], 1ull);
-        p.ovf_rows[at] = (unsigned)rows[r];
+        p.ovf_rows[at] = src.rowid(r);
       }
     }
     // accumulators (update_accumulators, aggregate.rs:548-612): argument evaluated once per row
     for (int g = 0; g < p.nargs; g++) {
-      unsigned long long v[AG_R];
+      unsigned long long v[R];
       unsigned av;
-      const unsigned b = eval_program_n<DEPTH, AG_R, false, NULLS>(p.ps, p.nkeys + g, src, v, av);
+      const unsigned b = src.arg(p, g, v, av);
       for (int a = 0; a < p.naggs; a++) {
         if (p.agg_arg[a] != g) continue;
-        const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
+        const int func = p.aggs[a].func, mt = p.aggs[a].mtype, l = p.t.loc[a];
+        const bool cond = p.cond_mm && l >= 1 && l <= 3 && (func == DFGPU_AGG_MIN || func == DFGPU_AGG_MAX);
 #pragma unroll
-        for (int r = 0; r < AG_R; r++) {
+        for (int r = 0; r < R; r++) {
           if (NULLS && func == DFGPU_AGG_COUNT && !((av >> r) & 1u)) continue;  // COUNT counts non-null values
           if (FRONT && fslot[r] >= 0) {
             acc_fold_shared(func, mt, &ftab[(1 + a) * FS + fslot[r]], v[r]);
             if ((b >> r) & 1u) bad = true;
           } else if (slot[r] >= 0) {
-            acc_fold_global(func, mt, p.t.val(slot[r], a), v[r]);
+            acc_fold_global_cond(func, mt, p.t.val(slot[r], a), v[r], cond && probing[r], cond ? line_word(ln[r], l) : 0ull);
             if ((b >> r) & 1u) bad = true;
           }
         }
       }
     }
+    bad = bad || src.bad != 0;
     // one counter update per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
     if (lane == 0 && new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
-    __syncthreads();
   }
   if (FRONT) {
-    // merge this CTA's front table into the global table (new keys are always admitted here: the
-    // front table only exists when groups are few)
+    // merge this CTA's front table into the global table.  New keys are always admitted here; the host
+    // lowers max_groups of a FRONT launch by grid x front slots, so the table stays at most half full.
     __syncthreads();
     unsigned new_groups = 0;
     for (int i = threadIdx.x; i < FS * ftables; i += AG_THREADS) {
@@ -345,7 +559,9 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
       const unsigned long long key = tb[j];
       if (key == EMPTY_KEY) continue;
       const unsigned long long h = mix64(key) & hmask;
-      const long long slot = probe_insert(p.t, p.cap, key, __ldcg(p.t.key((long long)h)), h, false, new_groups);
+      Line ln;
+      load_line<false>(p.t, (long long)h, ln);
+      const long long slot = probe_insert<false>(p.t, p.cap, key, ln, h, false, new_groups);
       if (slot < 0) { p.counters[3] = 2ull; continue; }
       for (int a = 0; a < p.naggs; a++)
         acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.t.val(slot, a), tb[(1 + a) * FS + j]);
@@ -353,6 +569,17 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
     if (new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
   }
   if (bad) p.counters[3] = 1ull;
+}
+
+template <int DEPTH, bool FRONT, bool NULLS>
+__global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__ AggParams p) {
+  extern __shared__ unsigned long long s_front[];  // FRONT: keys[AG_FRONT_SLOTS] then vals[naggs][AG_FRONT_SLOTS]
+  hash_agg_body<InterpSrc<DEPTH, NULLS>, FRONT, NULLS>(p, s_front);
+}
+template <bool FRONT>
+__global__ void __launch_bounds__(AG_THREADS) k_hash_agg_plain(const __grid_constant__ AggParams p) {
+  extern __shared__ unsigned long long s_front[];
+  hash_agg_body<PlainSrc, FRONT, false>(p, s_front);
 }
 
 // K4: no GROUP BY.  Per-thread accumulators live in shared memory (one 8-byte cell per thread per
@@ -370,6 +597,7 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
   unsigned nn[kMaxAggs];
 #pragma unroll
   for (int a = 0; a < kMaxAggs; a++) nn[a] = 0;
+  unsigned npass = 0;  // rows that passed the fused predicate (counters[6]: an aggregate over zero rows is null)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int a = 0; a < p.naggs; a++) s_acc[a][tid] = agg_identity(p.aggs[a].func);
   bool bad = false;
@@ -383,11 +611,23 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
       rows[r] = i < p.nrows ? i : -1;
       if (i < p.nrows) src.valid |= 1u << r;
     }
+    unsigned rmask = src.valid;  // rows that pass the fused WHERE predicate (program 0)
+    if (p.has_pred) {
+      unsigned long long v[RD_R];
+      unsigned pv;
+      const unsigned b = eval_program_n<DEPTH, RD_R, false, NULLS>(p.ps, 0, src, v, pv);
+      bad = bad || (b != 0);
+      unsigned keep = 0;
+#pragma unroll
+      for (int r = 0; r < RD_R; r++) keep |= (unsigned)(v[r] & 1ull) << r;
+      rmask &= keep;
+    }
+    if (p.has_pred) npass += __popc(rmask);
     for (int g = 0; g < p.nargs; g++) {
       unsigned long long v[RD_R];
       unsigned av;
-      const unsigned b = eval_program_n<DEPTH, RD_R, false, NULLS>(p.ps, g, src, v, av);
-      bad = bad || (b != 0);
+      const unsigned b = eval_program_n<DEPTH, RD_R, false, NULLS>(p.ps, p.has_pred + g, src, v, av);
+      bad = bad || ((b & rmask) != 0);
 #pragma unroll
       for (int a = 0; a < kMaxAggs; a++) {
         if (a >= p.naggs || p.agg_arg[a] != g) continue;
@@ -395,9 +635,9 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
         unsigned long long acc = s_acc[a][tid];
 #pragma unroll
         for (int r = 0; r < RD_R; r++)
-          if (rows[r] >= 0 && (!NULLS || ((av >> r) & 1u))) acc = acc_fold(func, mt, acc, v[r]);
+          if (((rmask >> r) & 1u) && (!NULLS || ((av >> r) & 1u))) acc = acc_fold(func, mt, acc, v[r]);
         s_acc[a][tid] = acc;
-        if (NULLS) nn[a] += __popc(av & src.valid);
+        if (NULLS) nn[a] += __popc(av & rmask);
       }
     }
   }
@@ -424,6 +664,11 @@ __global__ void __launch_bounds__(AG_THREADS) k_reduce(const __grid_constant__ A
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (lane == 0 && c && a < p.naggs) atomicAdd(&p.counters[8 + a], (unsigned long long)c);
     }
+  }
+  if (p.has_pred) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) npass += __shfl_xor_sync(0xffffffffu, npass, o);
+    if (lane == 0 && npass) atomicAdd(&p.counters[6], (unsigned long long)npass);
   }
   if (bad) p.counters[3] = 1ull;
 }
@@ -580,7 +825,9 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
       slot = p.cap;
     } else {
       const unsigned long long h = mix64(key) & hmask;
-      slot = probe_insert(p.t, p.cap, key, __ldcg(p.t.key((long long)h)), h, false, new_groups);
+      Line ln;
+      load_line<false>(p.t, (long long)h, ln);
+      slot = probe_insert<false>(p.t, p.cap, key, ln, h, false, new_groups);
       if (slot < 0) { p.counters[3] = 2ull; continue; }  // cannot happen: caller sizes the table
     }
     for (int a = 0; a < p.naggs; a++)
@@ -664,8 +911,9 @@ struct dfgpu_aggstate {
   // table
   long long cap = 0;
   long long expected = 0;
-  TableLayout t{nullptr, 0, 0, 0};
-  bool aos = false;
+  TableLayout t{};
+  bool aos = false;        // "line" layout: every accumulator shares the line with the key (tables beyond L2)
+  std::vector<dfgpu_insn> pred_prog;  // fused WHERE predicate (dfgpu_aggregate_set_predicate); empty = none
   bool use_front = false;  // route rows through the per-CTA shared-memory front table
   // Utf8 GROUP BY key (aggregate.rs:842-847): grouped by a 64-bit string hash; the last accumulator is a
   // hidden MIN(source << 40 | row) = representative row of the group; the key columns of all batches are
@@ -744,18 +992,53 @@ long long estimate_groups(long long d, long long s, long long total_rows) {
   return g > double(total_rows) ? total_rows : (long long)g;
 }
 
-bool want_aos(long long groups, int naggs) { return groups * 32 * (1 + naggs) > AG_SOA_L2_BUDGET; }
+// Bytes the scan keeps hot in L2 with the hybrid layout: one sector (or lw/4) per group for the line, and
+// every sector of each additive array once a quarter of its slots is in use.  Beyond the budget the table
+// is built in "line" form (one sector per group, whatever the number of aggregates).
+bool hybrid_enabled() {
+  static const bool off = getenv("DFGPU_AGG_HYBRID") && atoi(getenv("DFGPU_AGG_HYBRID")) == 0;  // A/B switch: 0 = plain SoA (round-1 layout)
+  return !off;
+}
+void layout_shape(const std::vector<AggDesc>& descs, int naggs, int nkeys, bool line_mode, long long* lw, int* n_add, signed char* loc) {
+  *lw = 1;
+  *n_add = 0;
+  if (nkeys > 0 && line_mode) {
+    while (*lw < 1 + naggs) *lw <<= 1;
+    for (int a = 0; a < naggs; a++) loc[a] = (signed char)(1 + a);
+    return;
+  }
+  int nmm = 0;
+  for (int a = 0; a < naggs; a++) {
+    const bool mm = descs[size_t(a)].func == DFGPU_AGG_MIN || descs[size_t(a)].func == DFGPU_AGG_MAX;
+    if (nkeys > 0 && mm && hybrid_enabled()) loc[a] = (signed char)(1 + nmm++);
+    else loc[a] = (signed char)~((*n_add)++);
+  }
+  while (*lw < 1 + nmm) *lw <<= 1;
+}
+bool want_aos(long long groups, const std::vector<AggDesc>& descs, int naggs) {
+  static const char* force = getenv("DFGPU_AGG_LAYOUT");  // A/B switch: "line" | "hybrid"
+  if (force && std::string(force) == "line") return true;
+  if (force && std::string(force) == "hybrid") return false;
+  long long lw;
+  int n_add;
+  signed char loc[kMaxAggs];
+  layout_shape(descs, naggs, 1, false, &lw, &n_add, loc);
+  const long long cap = std::max(AG_MIN_CAP, next_pow2(2 * groups));
+  const long long line_hot = groups * std::max<long long>(32, 8 * lw);
+  const long long arr_hot = std::min(cap * 8, groups * 32);
+  return line_hot + n_add * arr_hot > AG_SOA_L2_BUDGET;
+}
 
-TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, const std::vector<AggDesc>& descs, long long cap, bool aos) {
+TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, int nkeys, const std::vector<AggDesc>& descs, long long cap, bool aos) {
   InitParams ip;
   memset(&ip, 0, sizeof(ip));
-  long long w = 1;
-  while (w < 1 + naggs) w <<= 1;
-  const long long words = aos ? (cap + 1) * w : (cap + 1) * (1 + naggs);
-  ip.t.base = (unsigned long long*)ctx->alloc(size_t(words) * 8);
-  ip.t.sstride = aos ? w : 1;
-  ip.t.voff = aos ? 1 : cap + 1;
-  ip.t.astride = aos ? 1 : cap + 1;
+  int n_add = 0;
+  layout_shape(descs, naggs, nkeys, aos, &ip.t.lw, &n_add, ip.t.loc);
+  const size_t line_words = size_t(cap + 1) * size_t(ip.t.lw);
+  const size_t words = line_words + size_t(n_add) * size_t(cap + 1);
+  ip.t.base = (unsigned long long*)ctx->alloc(words * 8);  // >= 256-byte aligned: lines of up to 32 bytes never straddle a sector
+  ip.t.add = ip.t.base + line_words;
+  ip.t.astride = cap + 1;
   ip.nslots = cap + 1;
   ip.naggs = naggs;
   for (int a = 0; a < naggs; a++) ip.ident[a] = agg_identity(descs[size_t(a)].func);
@@ -765,11 +1048,11 @@ TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, const std::vector<AggDesc>& d
   return ip.t;
 }
 
-void read_counters(dfgpu_aggstate* st, unsigned long long* host4) {
+void read_counters(dfgpu_aggstate* st, unsigned long long* host8) {
   dfgpu_ctx* ctx = st->ctx;
-  DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters, 64, cudaMemcpyDeviceToHost, ctx->stream));
   DF_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int i = 0; i < 4; i++) host4[i] = ctx->h_scratch[8 + i];
+  for (int i = 0; i < 8; i++) host8[i] = ctx->h_scratch[8 + i];
 }
 
 int grid_for(dfgpu_ctx* ctx, long long work_items, int per_block, int blocks_per_sm) {
@@ -783,8 +1066,8 @@ int grid_for(dfgpu_ctx* ctx, long long work_items, int per_block, int blocks_per
 // grow the table to new_cap, re-inserting every occupied slot
 void table_grow(dfgpu_aggstate* st, long long new_cap) {
   dfgpu_ctx* ctx = st->ctx;
-  const bool aos = st->aos || want_aos(std::max(st->ngroups, new_cap / 8), st->naggs);
-  TableLayout nt = table_alloc(ctx, st->naggs, st->descs, new_cap, aos);
+  const bool aos = st->aos || want_aos(std::max(st->ngroups, new_cap / 8), st->descs, st->naggs);
+  TableLayout nt = table_alloc(ctx, st->naggs, st->nkeys, st->descs, new_cap, aos);
   // compact raw, then merge into the new table
   const size_t cnt = size_t(st->ngroups + 1);
   unsigned long long* ck = (unsigned long long*)ctx->alloc(cnt * 8);
@@ -834,25 +1117,29 @@ void table_grow(dfgpu_aggstate* st, long long new_cap) {
   st->cap = new_cap;
 }
 
-template <int DEPTH, bool FRONT, bool NULLS = false>
-void launch_hash_agg_f(dfgpu_ctx* ctx, const AggParams& p, long long n) {
-  const size_t smem = FRONT ? size_t(AG_FRONT_SLOTS) * 8 * size_t(1 + p.naggs) : 0;
-  auto kern = k_hash_agg<DEPTH, FRONT, NULLS>;
-  if (FRONT && ctx->first_use((const void*)kern))
+// Launch one scan kernel.  FRONT launches admit the keys of every CTA's front table unconditionally when
+// the CTA retires, so the fill limit of the global path is lowered by what they can add (grid x front
+// slots): the table stays at most half full and the front merge always finds a slot.
+template <class Kern>
+void launch_scan(dfgpu_ctx* ctx, Kern kern, AggParams& p, long long n, bool front) {
+  const size_t smem = front ? size_t(AG_FRONT_SLOTS) * 8 * size_t(1 + p.naggs) : 0;
+  if (front && ctx->first_use((const void*)kern))
     DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_FRONT_SLOTS * 8 * (1 + kMaxAggs)));
   int per_sm = 0;
   DF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, AG_THREADS, smem));
   if (per_sm < 1) per_sm = 1;
+  const int grid = grid_for(ctx, n, AG_TILE, per_sm);
+  if (front) p.max_groups = std::max<long long>(0, p.max_groups - (long long)grid * AG_FRONT_SLOTS);
   const int ps = ctx->prof_begin();
-  kern<<<grid_for(ctx, n, AG_TILE, per_sm), AG_THREADS, smem, ctx->stream>>>(p);
+  kern<<<grid, AG_THREADS, smem, ctx->stream>>>(p);
   DF_CUDA(cudaGetLastError());
   ctx->prof_end(ps);
   ctx->launches++;
 }
 template <int DEPTH>
-void launch_hash_agg(dfgpu_ctx* ctx, const AggParams& p, long long n, bool front) {
-  if (front) launch_hash_agg_f<DEPTH, true>(ctx, p, n);
-  else launch_hash_agg_f<DEPTH, false>(ctx, p, n);
+void launch_hash_agg(dfgpu_ctx* ctx, AggParams& p, long long n, bool front) {
+  if (front) launch_scan(ctx, k_hash_agg<DEPTH, true, false>, p, n, true);
+  else launch_scan(ctx, k_hash_agg<DEPTH, false, false>, p, n, false);
 }
 template <int DEPTH, bool NULLS = false>
 void launch_reduce(dfgpu_ctx* ctx, const AggParams& p, long long n) {
@@ -897,6 +1184,14 @@ extern "C" int dfgpu_aggregate_create(dfgpu_ctx* ctx, const dfgpu_insn* const* k
   });
 }
 
+extern "C" int dfgpu_aggregate_set_predicate(dfgpu_aggstate* st, const dfgpu_insn* pred, int pred_len) {
+  return guarded([&] {
+    if (!st || (pred_len > 0 && !pred)) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_set_predicate: null argument");
+    if (st->rows_seen > 0 || st->typed) fail(DFGPU_ERR_GENERAL, "the predicate must be set before the first batch");
+    st->pred_prog.assign(pred, pred + (pred_len > 0 ? pred_len : 0));
+  });
+}
+
 extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
   return guarded([&] {
     if (!st || !batch) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_update: null argument");
@@ -910,6 +1205,12 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     memset(&p, 0, sizeof(p));
     ProgramBuilder pb(batch);
     std::vector<int> kdt;
+    // fused WHERE: program 0 (FilterRelation under the aggregate, context.rs:126-139)
+    const int has_pred = st->pred_prog.empty() ? 0 : 1;
+    if (has_pred) {
+      const int pi = pb.add(st->pred_prog.data(), int(st->pred_prog.size()), "filter expression");
+      if (pb.out_dtype(pi) != DFGPU_BOOL) fail(DFGPU_ERR_EXECUTION, "Filter expression did not evaluate to boolean");  // filter.rs:62-67
+    }
     // a single plain Utf8 column as the key: group by a 64-bit hash of the strings (see dfgpu_aggstate)
     const DevColumn* ukey = nullptr;
     if (st->nkeys == 1 && st->key_progs[0].size() == 1 && st->key_progs[0][0].op == DFGPU_OP_COL && st->key_progs[0][0].col >= 0 &&
@@ -949,7 +1250,7 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       int pi;
       if (same >= 0) {
         agg_arg[size_t(a)] = agg_arg[size_t(same)];
-        pi = st->nkeys + agg_arg[size_t(a)];
+        pi = has_pred + st->nkeys + agg_arg[size_t(a)];
       } else {
         pi = pb.add(st->arg_progs[size_t(a)].data(), int(st->arg_progs[size_t(a)].size()), "aggregate argument");
         agg_arg[size_t(a)] = nargs++;
@@ -1010,8 +1311,8 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       if (st->nkeys == 1) st->key_mask[0] = ~0ull;  // single key: keep the sign-extended 64-bit value
       st->typed = true;
       st->cap = st->nkeys == 0 ? 0 : std::max(AG_MIN_CAP, next_pow2(2 * st->expected));
-      st->aos = st->nkeys > 0 && want_aos(st->expected, st->naggs);
-      st->t = table_alloc(ctx, st->naggs, st->descs, st->cap, st->aos);
+      st->aos = st->nkeys > 0 && want_aos(st->expected, st->descs, st->naggs);
+      st->t = table_alloc(ctx, st->naggs, st->nkeys, st->descs, st->cap, st->aos);
     } else {
       if (kdt != st->key_dtypes) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
       for (int a = 0; a < st->naggs; a++)
@@ -1039,18 +1340,25 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     }
     p.nrows = batch->nrows;
     p.counters = st->d_counters;
+    p.has_pred = has_pred;
+    {
+      static const bool no_cond = getenv("DFGPU_AGG_COND_MM") && atoi(getenv("DFGPU_AGG_COND_MM")) == 0;  // A/B switch
+      p.cond_mm = no_cond ? 0 : 1;
+    }
     const int d = p.ps.max_depth;
 
     if (st->nkeys == 0) {
       p.t = st->t;
       p.cap = 0;
+      if (has_pred) DF_CUDA(cudaMemsetAsync(st->d_counters + 6, 0, 8, ctx->stream));  // rows passing the predicate
       if (p.ps.has_nulls) {
         st->saw_nulls = true;
         launch_reduce<8, true>(ctx, p, p.nrows);
       } else {
-        for (int a = 0; a < st->naggs; a++) st->nonnull_host[size_t(a)] += batch->nrows;
+        if (!has_pred)
+          for (int a = 0; a < st->naggs; a++) st->nonnull_host[size_t(a)] += batch->nrows;
         // fast path: every distinct argument is a plain Float64 column
-        bool plain = true;
+        bool plain = !has_pred;
         ReduceF64Params rp;
         memset(&rp, 0, sizeof(rp));
         for (int g = 0; g < nargs && plain; g++) {
@@ -1075,10 +1383,71 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         else if (d <= 4) launch_reduce<4>(ctx, p, p.nrows);
         else launch_reduce<8>(ctx, p, p.nrows);
       }
-      unsigned long long c[4];
+      unsigned long long c[8];
       read_counters(st, c);
       if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
+      if (has_pred && !p.ps.has_nulls)  // null-free inputs: every row that passed the predicate is a non-null input
+        for (int a = 0; a < st->naggs; a++) st->nonnull_host[size_t(a)] += (long long)c[6];
       return;
+    }
+
+    // Plain-column fast path: keys and arguments are plain 4/8-byte columns, the WHERE clause (if any) a
+    // chain of column comparisons -> the interpreter-free kernel with 128-bit loads.
+    bool use_plain = false;
+    {
+      static const bool off = getenv("DFGPU_AGG_PLAIN") && atoi(getenv("DFGPU_AGG_PLAIN")) == 0;  // A/B switch
+      PlainSpec sp;
+      memset(&sp, 0, sizeof(sp));
+      auto wide = [](int dt) {
+        return dt == DFGPU_FLOAT64 || dt == DFGPU_INT64 || dt == DFGPU_UINT64 || dt == DFGPU_FLOAT32 || dt == DFGPU_INT32 || dt == DFGPU_UINT32;
+      };
+      bool ok = !off && !p.ps.has_nulls && p.ps.ncols <= 4;
+      for (int c = 0; ok && c < p.ps.ncols; c++)
+        ok = wide(p.ps.cols[c].dtype) && (reinterpret_cast<uintptr_t>(p.ps.cols[c].ptr) & 15) == 0;
+      for (int k = 0; ok && k < st->nkeys; k++) {
+        const CompiledProgram& cpk = pb.prog(has_pred + k);
+        ok = cpk.is_plain_column;
+        sp.key_slot[k] = cpk.plain_slot;
+      }
+      for (int g = 0; ok && g < nargs; g++) {
+        const CompiledProgram& cpa = pb.prog(has_pred + st->nkeys + g);
+        ok = cpa.is_plain_column;
+        sp.arg_slot[g] = cpa.plain_slot;
+      }
+      if (ok && has_pred) {
+        // t0 [t1 AND|OR [t2 AND|OR ...]] in lowered form: (PUSH_COL, CMP leaf) {(PUSH_COL, CMP leaf), AND|OR stack}*
+        const int b = p.ps.start[0], e = p.ps.start[1];
+        const DevInsn* in = &p.ps.insn[b];
+        auto term_at = [&](int i, PlainTerm* out) {
+          if (i + 1 >= e - b) return false;
+          const DevInsn &c = in[i], &o = in[i + 1];
+          if (c.op != V_PUSH_COL) return false;
+          if (o.op < V_EQ || o.op > V_GE || o.mode == RHS_STACK) return false;
+          if (o.mode == RHS_COL && p.ps.cols[o.slot].dtype != p.ps.cols[c.slot].dtype) return false;
+          memset(out, 0, sizeof(*out));
+          out->kind = o.mode == RHS_COL ? 2 : 3;
+          out->op = o.op;
+          out->a = c.slot;
+          out->b = o.mode == RHS_COL ? o.slot : 0;
+          out->mt = mtype_of(p.ps.cols[c.slot].dtype);
+          out->imm = o.imm;
+          return true;
+        };
+        ok = term_at(0, &sp.term[0]);
+        sp.nterms = ok ? 1 : 0;
+        int i = 2;
+        while (ok && i < e - b) {
+          if (sp.nterms >= 4 || !term_at(i, &sp.term[sp.nterms]) || i + 2 >= e - b) { ok = false; break; }
+          const DevInsn& j = in[i + 2];
+          if ((j.op != V_AND && j.op != V_OR) || j.mode != RHS_STACK) { ok = false; break; }
+          sp.term[sp.nterms].conn = j.op == V_OR ? 1 : 0;
+          sp.nterms++;
+          i += 3;
+        }
+      }
+      sp.ncols = p.ps.ncols;
+      if (ok) p.plain = sp;
+      use_plain = ok;
     }
 
     // GROUP BY: run, then replay rows that could not get a slot after growing the table.
@@ -1126,44 +1495,17 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
           static const bool no_hint = getenv("DFGPU_AGG_STREAM_HINT") && atoi(getenv("DFGPU_AGG_STREAM_HINT")) == 0;  // A/B switch
           p.stream_hint = no_hint ? 0 : 1;
         }
-        // Experiment (default off, DFGPU_AGG_L2_PERSIST=1): pin the table in the
-        // persisting part of L2 for the scan, let everything else stream.
-        static const bool l2_persist = getenv("DFGPU_AGG_L2_PERSIST") && atoi(getenv("DFGPU_AGG_L2_PERSIST")) != 0;
-        if (l2_persist) {
-          cudaDeviceProp prop;
-          DF_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
-          const size_t tbytes = size_t(st->cap + 1) * 8 * size_t(st->aos ? st->t.sstride : 1 + st->naggs);
-          const size_t window = std::min(tbytes, size_t(prop.accessPolicyMaxWindowSize));
-          const size_t carve = std::min(window, size_t(prop.persistingL2CacheMaxSize));
-          if (carve > 0) {
-            DF_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof(av));
-            av.accessPolicyWindow.base_ptr = st->t.base;
-            av.accessPolicyWindow.num_bytes = window;
-            av.accessPolicyWindow.hitRatio = float(double(carve) / double(window));
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            DF_CUDA(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
-          }
-        }
-        struct L2Reset {
-          dfgpu_ctx* c;
-          bool on;
-          ~L2Reset() {
-            if (!on) return;
-            cudaStreamAttrValue av;
-            memset(&av, 0, sizeof(av));
-            cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-            cudaCtxResetPersistingL2Cache();
-          }
-        } l2_reset{ctx, l2_persist};
-        if (p.ps.has_nulls) launch_hash_agg_f<8, false, true>(ctx, p, n);
-        else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
+        // (A persisting-L2 access-policy window over the table was measured in round 2 and removed: the scan
+        // went from 1.57 to 7.8 ms at 1e5 groups and from 3.4 to 15 ms at 1e6, profiles/r02a_l2persist.txt.)
+        if (p.ps.has_nulls) launch_scan(ctx, k_hash_agg<8, false, true>, p, n, false);
+        else if (use_plain && !list && (p.row_begin & 1) == 0) {
+          if (front) launch_scan(ctx, k_hash_agg_plain<true>, p, n, true);
+          else launch_scan(ctx, k_hash_agg_plain<false>, p, n, false);
+        } else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
         else if (d <= 4) launch_hash_agg<4>(ctx, p, n, front);
         else launch_hash_agg<8>(ctx, p, n, front);
-        unsigned long long c[4];
+        unsigned long long c[8];
         read_counters(st, c);
         if (c[3] == 2) fail(DFGPU_ERR_INTERNAL, "front-table merge could not find a slot");
         if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
@@ -1190,7 +1532,7 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         const long long afford = (long long)(ctx->device_mem_bytes / 8) / (32 * (1 + st->naggs));  // slots that fit in 1/8 of device memory
         long long want_cap = std::max(AG_MIN_CAP, next_pow2(est * 2));
         while (want_cap > st->cap && want_cap > afford) want_cap >>= 1;
-        const bool to_aos = !st->aos && want_aos(est, st->naggs);
+        const bool to_aos = !st->aos && want_aos(est, st->descs, st->naggs);
         if (to_aos || want_cap > st->cap) {
           st->aos = st->aos || to_aos;
           table_grow(st, std::max(st->cap, want_cap));
@@ -1303,7 +1645,7 @@ void dfgpu::agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, co
   k_merge<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mp);
   DF_CUDA(cudaGetLastError());
   ctx->launches++;
-  unsigned long long c[4];
+  unsigned long long c[8];
   read_counters(st, c);
   if (c[3]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed");
   st->ngroups = (long long)c[0];
@@ -1335,7 +1677,7 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       }
       st->typed = true;
       st->cap = 0;
-      st->t = table_alloc(ctx, st->naggs, st->descs, 0, false);
+      st->t = table_alloc(ctx, st->naggs, st->nkeys, st->descs, 0, false);
     }
     if (ctx->world > 1) {
       // every rank must take part, and ranks reduce row counts too (null-ness of the global result)

@@ -69,6 +69,7 @@ def lib():
     L.dfgpu_filter_project_host.argtypes = [vp, C.POINTER(A.Col), C.c_int, PI, C.c_int, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.c_int64, C.POINTER(vp)]
     L.dfgpu_result_col_host_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
     L.dfgpu_aggregate_create.argtypes = [vp, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(A.Agg), C.c_int, C.c_int64, C.POINTER(vp)]
+    L.dfgpu_aggregate_set_predicate.argtypes = [vp, PI, C.c_int]
     L.dfgpu_aggregate_update.argtypes = [vp, vp]
     L.dfgpu_aggregate_finish.argtypes = [vp, C.POINTER(vp)]
     L.dfgpu_aggregate_free.argtypes = [vp]
@@ -260,7 +261,8 @@ class GpuContext:
         return Result(self, out)
 
     # -- AggregateRelation ------------------------------------------------------------------------
-    def aggregate(self, batches, keys=(), aggs=(), expected_groups=0):
+    def aggregate(self, batches, keys=(), aggs=(), expected_groups=0, pred=None):
+        """AggregateRelation over `batches`; `pred` = the WHERE clause of a Selection under it, fused into the scan."""
         if isinstance(batches, Batch):
             batches = [batches]
         schema = batches[0].schema
@@ -270,6 +272,10 @@ class GpuContext:
         st = C.c_void_p()
         check(lib().dfgpu_aggregate_create(self.h, kptrs, klens, nk, aggarr, len(aggs), expected_groups, C.byref(st)))
         try:
+            if pred is not None:
+                pprog = pred.program(schema)
+                parr = (A.Insn * max(1, len(pprog)))(*pprog)
+                check(lib().dfgpu_aggregate_set_predicate(st, parr, len(pprog)))
             for b in batches:
                 check(lib().dfgpu_aggregate_update(st, b.h))
             out = C.c_void_p()

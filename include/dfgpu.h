@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DFGPU_ABI_VERSION 1
+#define DFGPU_ABI_VERSION 2
 
 /* ---- error codes (→ ExecutionError variants, src/execution/error.rs:51-60) ---- */
 enum {
@@ -201,6 +201,13 @@ int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, 
 int dfgpu_aggregate_create(dfgpu_ctx* ctx, const dfgpu_insn* const* keys, const int* key_len, int nkeys,
                            const dfgpu_agg* aggs, int naggs, int64_t expected_groups /*0 = unknown*/,
                            dfgpu_aggstate** out);
+/* FilterRelation fused under the aggregate: the wiring `Aggregate{input: Selection{expr, ..}}` that
+ * ExecutionContext::execute builds for `SELECT .. WHERE .. GROUP BY ..` (src/execution/context.rs:126-139,
+ * 162-192; src/sqlplanner.rs:93-96).  The predicate (a Boolean postfix program over the SAME input columns,
+ * else "Filter expression did not evaluate to boolean": filter.rs:62-67) is evaluated inside the scan
+ * kernel before the probe: one pass over the input, no intermediate batch.  Must be called before the
+ * first dfgpu_aggregate_update; pred_len == 0 removes it. */
+int dfgpu_aggregate_set_predicate(dfgpu_aggstate* st, const dfgpu_insn* pred, int pred_len);
 int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* batch);
 int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out);
 int dfgpu_aggregate_free(dfgpu_aggstate* st);

@@ -33,12 +33,12 @@ def gpu_fp(ctx, arrays, pred, proj):
         b.free()
 
 
-def gpu_agg(ctx, arrays, keys, aggs, nbatches=1, expected=0):
+def gpu_agg(ctx, arrays, keys, aggs, nbatches=1, expected=0, pred=None):
     n = len(arrays[0])
     bounds = [int(x) for x in np.linspace(0, n, nbatches + 1)]
     batches = [ctx.upload([a[bounds[i]:bounds[i + 1]] for a in arrays]) for i in range(nbatches)]
     try:
-        r = ctx.aggregate(batches, keys, aggs, expected)
+        r = ctx.aggregate(batches, keys, aggs, expected, pred=pred)
         try:
             return r.columns()
         finally:
@@ -387,6 +387,79 @@ def test_groupby_high_cardinality_layouts(ctx):
     assert np.array_equal(got[0], uk) and np.array_equal(got[4], np.bincount(inv).astype(np.uint64))
 
 
+def oracle_filtered_aggregate(arrays, pred, keys, aggs):
+    """The reference's wiring for WHERE + GROUP BY: FilterRelation (gathers every column) feeding
+    AggregateRelation (context.rs:126-139, 162-192)."""
+    kept = O.filter_project(arrays, pred, [col(i) for i in range(len(arrays))])
+    return O.aggregate(kept, keys, aggs)
+
+
+def test_groupby_fused_where_vs_oracle(ctx):
+    # SELECT k, MIN(v), MAX(v), SUM(v), COUNT(v) FROM g WHERE <pred> GROUP BY k: the predicate runs inside the
+    # scan kernel.  Comparison chains take the interpreter-free kernel, arithmetic predicates the interpreter.
+    n = 1_000_000
+    arrays, keys, aggs, _ = workloads.c5(n, nkeys=20_000)
+    aggs = aggs + [AggregateFunction("count", col(1))]
+    preds = [col(1) < lit(0.25),
+             (col(1) > lit(0.1)) & (col(1) < lit(0.9)),
+             (col(1) < lit(0.05)) | (col(1) >= lit(0.95)),
+             (col(1) * lit(2.0)) < lit(0.5),
+             col(1) < lit(-1.0)]  # nothing passes: empty result
+    for pred in preds:
+        exp = oracle_filtered_aggregate(arrays, pred, keys, aggs)
+        for nb in [1, 3]:
+            got = gpu_agg(ctx, arrays, keys, aggs, nbatches=nb, pred=pred)
+            check_groupby(got, exp, 1, exact_cols={0, 1, 2, 4}, sum_cols={3})
+    # expression keys and arguments (interpreter path) under a predicate on another column
+    rng = np.random.default_rng(77)
+    k = rng.integers(0, 5000, n, dtype=np.int64)
+    w = rng.integers(-100, 100, n, dtype=np.int64)
+    v = rng.random(n)
+    keys2 = [col(0) + lit(7)]
+    aggs2 = [AggregateFunction("sum", col(2) * lit(3.0)), AggregateFunction("max", col(1)), AggregateFunction("count", col(2))]
+    pred2 = (col(1) > lit(-20)) & (col(2) < lit(0.75))
+    exp = oracle_filtered_aggregate([k, w, v], pred2, keys2, aggs2)
+    got = gpu_agg(ctx, [k, w, v], keys2, aggs2, pred=pred2)
+    check_groupby(got, exp, 1, exact_cols={0, 2, 3}, sum_cols={1})
+    # Int32 keys / Float32 arguments through the plain kernel's 4-byte loads, odd row count
+    k32 = rng.integers(0, 3000, n - 1, dtype=np.int32)
+    v32 = rng.random(n - 1).astype(np.float32)
+    aggs3 = [AggregateFunction("min", col(1)), AggregateFunction("max", col(1)), AggregateFunction("count", col(1))]
+    pred3 = col(1) >= lit(0.5, A.FLOAT32)
+    exp = oracle_filtered_aggregate([k32, v32], pred3, [col(0)], aggs3)
+    got = gpu_agg(ctx, [k32, v32], [col(0)], aggs3, pred=pred3)
+    check_groupby(got, exp, 1, exact_cols={0, 1, 2, 3}, sum_cols=set())
+
+
+def test_no_groupby_fused_where_vs_oracle(ctx):
+    n = 700_001
+    rng = np.random.default_rng(78)
+    v = rng.random(n)
+    w = rng.integers(0, 1000, n, dtype=np.int64)
+    aggs = [AggregateFunction("min", col(0)), AggregateFunction("max", col(0)), AggregateFunction("sum", col(0)), AggregateFunction("count", col(0)),
+            AggregateFunction("sum", col(1))]
+    for pred in [col(0) < lit(0.3), (col(1) >= lit(500)) & (col(0) > lit(0.5))]:
+        exp = oracle_filtered_aggregate([v, w], pred, [], aggs)
+        got = gpu_agg(ctx, [v, w], [], aggs, nbatches=2, pred=pred)
+        for i, (g, e) in enumerate(zip(got, exp)):
+            if i == 2:
+                np.testing.assert_allclose(g, e, rtol=SUM_RTOL)
+            else:
+                assert np.array_equal(g, e), i
+    # nothing passes: MIN / MAX / SUM are null, exactly as over an empty input
+    got = gpu_agg(ctx, [v, w], [], aggs[:3], pred=col(0) < lit(-1.0))
+    exp = oracle_filtered_aggregate([v, w], col(0) < lit(-1.0), [], aggs[:3])
+    for g, e in zip(got, exp):
+        assert isinstance(g, tuple) == isinstance(e, tuple)
+        if isinstance(g, tuple):
+            assert np.array_equal(g[1], e[1])
+    # a predicate that is not Boolean is the reference's FilterRelation error
+    with pytest.raises(engine.DfGpuError) as ei:
+        gpu_agg(ctx, [v, w], [], aggs[:1], pred=col(0) + lit(1.0))
+    assert "did not evaluate to boolean" in str(ei.value)
+
+
+
 def test_golden_group_by_string_min_max(ctx, golden, fmt_f64):
     # tests/sql.rs:55-67: GROUP BY a Utf8 column
     t = golden["aggregate_test_2"]
@@ -525,6 +598,41 @@ def test_c4_full_size_properties(ctx):
     assert np.array_equal(got[0], inv[order])
     assert np.array_equal(got[2], cnt[order].astype(np.uint64))
     np.testing.assert_allclose(got[1], sm[order], rtol=SUM_RTOL)
+
+
+def test_c3_full_size_parity(ctx):
+    # BASELINE configs[2] at its stated size: 1e8 rows x 4 Float64 columns, fused expr + filter, bit-exact vs numpy
+    n = 100_000_000
+    arrays, pred, proj = workloads.c3(n)
+    a, b = arrays[0], arrays[1]
+    bt = ctx.upload(arrays)
+    r = ctx.filter_project(bt, pred, proj)
+    out = r.columns()
+    r.free(); bt.free()
+    m = b < a
+    assert len(out[0]) == int(m.sum())
+    assert np.array_equal(out[0], (a + b)[m])  # one IEEE add / multiply per element: bit-exact, order-preserving
+    assert np.array_equal(out[1], (a * b)[m])
+
+
+def test_c5_full_size_parity(ctx):
+    # BASELINE configs[4] per-GPU shard at its stated size (1e9 rows / 8 GPUs = 1.25e8 rows, 1e6 keys):
+    # keys / MIN / MAX bit-exact, SUM within 1e-9 relative, vs pandas / numpy on the same rows
+    import pandas as pd
+    n = 125_000_000
+    arrays, keys, aggs, k_raw = workloads.c5(n)
+    got = sort_by_key(gpu_agg(ctx, arrays, keys, aggs))
+    v = arrays[1]
+    gb = pd.Series(v).groupby(k_raw, sort=True)
+    mn, mx = gb.min(), gb.max()
+    present = mn.index.to_numpy()
+    sm = np.bincount(k_raw, weights=v, minlength=1_000_000)[present]
+    mixed = workloads.mix_keys(present.astype(np.int64))
+    order = np.argsort(mixed)
+    assert np.array_equal(got[0], mixed[order])
+    assert np.array_equal(got[1], mn.to_numpy()[order]) and np.array_equal(got[2], mx.to_numpy()[order])
+    np.testing.assert_allclose(got[3], sm[order], rtol=SUM_RTOL)
+
 
 
 # ---------------------------------------------------------------------------------------------
