@@ -1,27 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — the hot path of BASELINE.json on B200: rows/s and fraction of HBM roofline.
+"""bench.py — the hot path of BASELINE.json on B200: rows/s and fraction of HBM roofline, filter AND aggregate.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Headline workload (BASELINE.json configs[1], "C2"): SELECT a FROM t WHERE a > 0.5 over 1e8
-synthetic Float64 rows per GPU — the fused predicate + order-preserving filter-gather kernel.
-A "step" is one pass of that operator over one 1e8-row batch.  Rows are partitioned by row range
-across ranks (no data-path collective for filter/project), so scaling is weak: every rank filters
-its own 1e8-row batch and `value` is the total rows of all ranks / max-over-ranks device time.
+Headline workload (BASELINE.json configs[1], "C2"): SELECT a FROM t WHERE a > 0.5 over 1e8 synthetic Float64
+rows per GPU — the fused predicate + order-preserving filter-gather kernel.  A "step" is one pass of that
+operator over one 1e8-row batch.  Rows are partitioned by row range across ranks (no data-path collective for
+filter/project), so scaling is weak: every rank filters its own 1e8-row batch and `value` is the total rows of
+all ranks / max-over-ranks device time.  The aggregate half of the metric (configs[3], "C4": SELECT k, SUM(v),
+COUNT(v) GROUP BY k over 1e8 rows / 1e5 Int64 keys) is measured with the same rules and reported at top level
+next to it (`roofline_c4`, `e2e_c4`, `cpu_baseline_c4`); C3 and C5 are in `extra`.
 
-  value     device-resident: the batch is already in HBM when the timed region starts
-  e2e       through the C ABI with HOST buffers (dfgpu_filter_project_host): H2D of the batch from
-            pinned memory, the kernel, and D2H of the compacted result into pinned memory, every step,
-            pipelined by row-range chunk inside the library
-  roofline  algorithmic bytes of the dominant kernel (8*N read + 8*N_sel written) / its average
-            duration measured with CUDA events recorded around the launch on the launching stream
-  extra     the other single-GPU BASELINE configs (C3 fused expr+filter, C4 hash GROUP BY; with N>1
-            C4 includes the NCCL partial-aggregate merge), same timing rules
-  cpu_baseline  the CPU oracle (C++ restatement of the reference's single-threaded operators) on a
-            bounded sample of the same workload, on this box's host cores (rank 0, N=1 only)
+  value         device-resident: the batch is already in HBM when the timed region starts
+  e2e           through the C ABI with HOST buffers (dfgpu_filter_project_host): H2D of the batch from pinned
+                memory, the kernel, and D2H of the compacted result into pinned memory, every step, pipelined
+                by row-range chunk inside the library
+  roofline      algorithmic bytes of the dominant kernel (8*N read + 8*N_sel written) / its average duration
+                measured with CUDA events recorded around the launch on the launching stream
+  sustained     the same resident step repeated back to back for >= 0.5 s (the K timed steps of C2 last a few ms)
+  roofline_c4   the same for k_hash_agg (16*N bytes read), e2e_c4 through dfgpu_aggregate_update_host
+  extra         C3 (fused expr+filter) and C5 (1e6 keys, MIN/MAX/SUM, 1.25e8 rows per GPU = 1e9 rows on 8 GPUs;
+                with N>1 C4 and C5 include the NCCL partial-aggregate merge), same timing rules
+  checks        every aggregate result (also the merged multi-GPU one, on every rank) is compared with numpy /
+                pandas on the same rows: key set, COUNT, MIN, MAX bit-exact, SUM within 1e-9; a mismatch fails the run
+  cpu_baseline  the CPU oracle (C++ restatement of the reference's single-threaded operators) on a bounded
+                sample of the same workload, on this box's host cores (rank 0, N=1 only)
 
---impl reference times that CPU restatement alone (the reference is Rust; no toolchain here).
+--impl reference times that CPU restatement alone (the reference is Rust; no toolchain here) on the SAME
+config: one full 1e8-row C2 batch per step.
 """
 import argparse
 import json
@@ -37,6 +44,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "rows/s filter+agg over 1e8-row Arrow batch (C2: SELECT a FROM t WHERE a>0.5, Float64)"
+SUM_RTOL = 1e-9
+
+
+def c2_config(n):
+    """The `config` object of both arms (the reference arm must describe exactly what ours measures)."""
+    return {"workload": "C2: SELECT a FROM t WHERE a > 0.5; a~U[0,1) Float64, %d rows per GPU, seed 42+rank" % n,
+            "rows_per_gpu": n, "partitioning": "row-range, one batch per rank, no collective",
+            "l2": "inputs (%.1f GB per step) larger than L2 (126 MB); no explicit flush" % (8.0 * n / 1e9)}
 
 
 def ncu_traffic(key):
@@ -136,7 +151,7 @@ class ClockSampler:
             reasons = sorted({nm for _, rs, _ in self.samples for nm, b in bits.items() if rs & b})
             sm = [x[0] for x in self.samples]
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "power_w_max": max([x[2] for x in self.samples], default=None),
-                    "samples": len(sm), "reasons": reasons, "source": "nvml, ~2 ms period, warm-up + timed steps"}
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, ~2 ms period, warm-up + timed steps + sustained loop"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -184,22 +199,31 @@ def barrier(torch):
         torch.cuda.synchronize()
 
 
-def max_over_ranks(torch, x):
+def _reduce(torch, x, op):
     if torch is None:
         return x
     import torch.distributed as dist
     t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
     return float(t.item())
+
+
+def max_over_ranks(torch, x):
+    return _reduce(torch, x, "MAX")
 
 
 def sum_over_ranks(torch, x):
+    return _reduce(torch, x, "SUM")
+
+
+def allreduce_np(torch, arr, op):
+    """Element-wise reduction of a numpy array over ranks (the CHECKER's path: torch.distributed, not the engine)."""
     if torch is None:
-        return x
+        return arr
     import torch.distributed as dist
-    t = torch.tensor([x], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    return float(t.item())
+    t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+    dist.all_reduce(t, op=getattr(dist.ReduceOp, op))
+    return t.cpu().numpy()
 
 
 def time_steps(ctx, torch, fn, steps, warmup):
@@ -221,6 +245,41 @@ def time_steps(ctx, torch, fn, steps, warmup):
     return max_over_ranks(torch, ms), kms, kn, ctx.kernel_launches() - l0
 
 
+def check_groupby(torch, got, k_raw, v, nkeys, want, what):
+    """Compare a (possibly merged, global) GROUP BY result with numpy / pandas on the same rows.  `got`: result
+    columns [key, aggregates...]; `want`: aggregate names in column order.  Dense per-key partials are computed
+    from this rank's rows and combined over ranks with torch.distributed (independent of the engine's merge)."""
+    from datafusion_archive_b200 import workloads
+    cnt = allreduce_np(torch, np.bincount(k_raw, minlength=nkeys).astype(np.int64), "SUM")
+    exp = {"count": cnt.astype(np.uint64)}
+    if "sum" in want:
+        exp["sum"] = allreduce_np(torch, np.bincount(k_raw, weights=v, minlength=nkeys), "SUM")
+    if "min" in want or "max" in want:
+        import pandas as pd
+        gb = pd.Series(v).groupby(k_raw, sort=True)
+        mn = np.full(nkeys, np.inf)
+        mx = np.full(nkeys, -np.inf)
+        g_mn, g_mx = gb.min(), gb.max()
+        mn[g_mn.index.to_numpy()] = g_mn.to_numpy()
+        mx[g_mx.index.to_numpy()] = g_mx.to_numpy()
+        exp["min"] = allreduce_np(torch, mn, "MIN")
+        exp["max"] = allreduce_np(torch, mx, "MAX")
+    present = np.nonzero(cnt)[0]
+    mixed = workloads.mix_keys(present.astype(np.int64))
+    order = np.argsort(mixed)
+    o = np.argsort(got[0])
+    assert len(got[0]) == len(present), "%s: %d groups, expected %d" % (what, len(got[0]), len(present))
+    assert np.array_equal(got[0][o], mixed[order]), what + ": key set differs"
+    for j, name in enumerate(want):
+        g, e = got[1 + j][o], exp[name][present][order]
+        if name == "sum":
+            np.testing.assert_allclose(g, e, rtol=SUM_RTOL, atol=0, err_msg=what + ": SUM")
+        else:
+            assert np.array_equal(g, e), "%s: %s differs" % (what, name.upper())
+    return {"groups": int(len(present)), "checked": [w for w in want], "against": "numpy bincount / pandas groupby on the same rows"
+            + ("; per-rank partials all-reduced with torch.distributed" if torch is not None else "")}
+
+
 def run_ours(args):
     from datafusion_archive_b200 import engine, workloads
     rank, world, local, torch = dist_setup(args.gpus)
@@ -229,7 +288,7 @@ def run_ours(args):
     ctx = engine.GpuContext(local)
     peak, peak_src = hbm_peak()
     n = args.rows
-    steps, warmup = args.steps, max(3, args.warmup)
+    steps, warmup = (args.steps or 2000), max(3, args.warmup)
 
     # ---- C2 (headline) -----------------------------------------------------------------------
     pin_in = engine.PinnedBuffer((n,), np.float64)
@@ -255,8 +314,11 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     ms, kms, kn, launches = time_steps(ctx, torch, step_resident, steps, warmup)
-    clocks = sampler.stop()
     assert state["nrows"] == n_sel, "GPU row count %d != expected %d" % (state["nrows"], n_sel)
+    # sustained: the same step back to back for >= 0.5 s (same kernel, clocks sampled throughout)
+    sus_steps = max(steps, int(np.ceil(600.0 / max(ms / steps, 1e-3))))
+    sms, skms, skn, _ = time_steps(ctx, torch, step_resident, sus_steps, 0)
+    clocks = sampler.stop()
     total_rows = sum_over_ranks(torch, float(n))
     value = total_rows * steps / (ms / 1e3)
     kernel_ms = kms / steps  # device time of the dominant kernel per step (1 launch per step here)
@@ -268,14 +330,12 @@ def run_ours(args):
     e2e_value = total_rows * e2e_steps / (ems / 1e3)
     batch.free()
 
+    cfg = c2_config(n)
+    cfg["selectivity"] = n_sel / n
     out = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": "C2: SELECT a FROM t WHERE a > 0.5; a~U[0,1) Float64, %d rows per GPU, seed 42+rank" % n,
-                   "rows_per_gpu": n, "selectivity": n_sel / n, "partitioning": "row-range, one batch per rank, no collective",
-                   "l2": "inputs (%.1f GB per step) larger than L2 (126 MB); no explicit flush" % (8.0 * n / 1e9)},
-        "clocks": clocks,
+        "data": "synthetic", "config": cfg, "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rows/s", "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 8 * n_sel + 32,
                 "steps": e2e_steps, "ms_per_step": ems / e2e_steps,
                 "path": "dfgpu_filter_project_host: pinned host batch -> chunked H2D | kernel | D2H pipeline -> pinned host result"},
@@ -283,14 +343,16 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("k_filter_project:c2") if n == 100_000_000 else None, "kernel": "k_filter_project_tma", "kernel_ms": kernel_ms,
                      "algorithmic_bytes": alg_bytes, "peak_source": peak_src},
+        "sustained": {"steps": sus_steps, "seconds": sms / 1e3, "ms_per_step": sms / sus_steps, "kernel_ms": skms / sus_steps,
+                      "value": total_rows * sus_steps / (sms / 1e3), "roofline_frac": alg_bytes / (skms / sus_steps / 1e3) / 1e9 / peak},
     }
 
-    # ---- extras: C3 and C4 (same timing rules; failures are recorded, not fatal) ----------------
+    # ---- C3 (extra) ---------------------------------------------------------------------------------
     extra = {}
     xs = max(3, min(steps, 10))
     try:
         arrays3, pred3, proj3 = workloads.c3(n, seed=142 + 10 * rank)
-        b3 = ctx.upload(arrays3)
+        b3 = ctx.upload(arrays3[:2])  # c, d are never referenced: not uploaded (the host layer prunes them the same way)
         sel3 = int(np.count_nonzero(arrays3[1] < arrays3[0]))
 
         def step3():
@@ -309,54 +371,93 @@ def run_ours(args):
         del arrays3
     except Exception as e:  # pragma: no cover
         extra["c3"] = {"error": repr(e)}
-    try:
-        arrays4, keys4, aggs4, _ = workloads.c4(n, seed=46 + 10 * rank)
-        b4 = ctx.upload(arrays4)
-        if world > 1:
-            import torch.distributed as dist
-            uid = [engine.comm_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            ctx.comm_init(rank, world, uid[0])
 
-        def step4():
-            r = ctx.aggregate(b4, keys4, aggs4)
-            state["g4"] = r.nrows
-            r.free()
-        ms4, kms4, kn4, _ = time_steps(ctx, torch, step4, xs, 3)
-        assert state["g4"] == 100_000, state["g4"]
-        k4 = kms4 / xs  # k_hash_agg runs twice per step on a first batch: 1 Mi-row sampled prefix + the rest
-        bytes4 = 16.0 * n
-        extra["c4"] = {"workload": "C4: SELECT k, SUM(v), COUNT(v) FROM t GROUP BY k; 1e5 Int64 keys" + (" + NCCL partial-aggregate merge" if world > 1 else ""),
-                       "value": total_rows * xs / (ms4 / 1e3), "unit": "rows/s", "ms_per_step": ms4 / xs, "kernel_ms": k4,
-                       "roofline": {"bound": "hbm", "achieved": bytes4 / (k4 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                    "frac": bytes4 / (k4 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes4, "kernel": "k_hash_agg"},
-                       "scatter_ceiling": scatter_ceiling(k4, n)}
-        b4.free()
-        del arrays4
-        # C5-style: 1e6 keys, MIN / MAX / SUM (the table no longer fits the hot part of L2)
-        arrays5, keys5, aggs5, _ = workloads.c5(n, seed=46 + 10 * rank)
+    # ---- C4 (the aggregate half of the metric: top level) and C5 (extra); a failed check fails the run ----
+    if world > 1:
+        import torch.distributed as dist
+        uid = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    merge = " + NCCL partial-aggregate merge (global result on every rank)" if world > 1 else ""
+
+    pin_k, pin_v = engine.PinnedBuffer((n,), np.int64), engine.PinnedBuffer((n,), np.float64)
+    arrays4, keys4, aggs4, kraw4 = workloads.c4(n, seed=46 + 10 * rank)
+    pin_k.array[:] = arrays4[0]
+    pin_v.array[:] = arrays4[1]
+    arrays4 = [pin_k.array, pin_v.array]
+    b4 = ctx.upload(arrays4)
+
+    def step4():
+        r = ctx.aggregate(b4, keys4, aggs4)
+        state["g4"] = r.nrows
+        if "keep4" in state:
+            state["cols4"] = r.columns()
+        r.free()
+
+    def step4_e2e():
+        r = ctx.aggregate_host(arrays4, keys4, aggs4)
+        state["g4e"] = r.nrows
+        state["cols4e"] = r.columns()  # D2H of the (small) result is part of the step
+        r.free()
+    ms4, kms4, kn4, _ = time_steps(ctx, torch, step4, xs, 3)
+    state["keep4"] = True
+    step4()
+    del state["keep4"]
+    chk4 = check_groupby(torch, state["cols4"], kraw4, arrays4[1], 100_000, ["sum", "count"], "C4")
+    k4 = kms4 / xs  # scan kernel time per step (a first batch runs two launches: 1 Mi-row sampled prefix + the rest)
+    bytes4 = 16.0 * n
+    out["roofline_c4"] = {"bound": "hbm", "achieved": bytes4 / (k4 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                          "frac": bytes4 / (k4 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes4, "kernel": "k_hash_agg_plain", "kernel_ms": k4,
+                          "traffic": ncu_traffic("k_hash_agg:c4") if n == 100_000_000 else None, "peak_source": peak_src,
+                          "scatter_ceiling": scatter_ceiling(k4, n)}
+    out["c4"] = {"workload": "C4: SELECT k, SUM(v), COUNT(v) FROM t GROUP BY k; 1e5 Int64 keys, %d rows per GPU%s" % (n, merge),
+                 "value": total_rows * xs / (ms4 / 1e3), "unit": "rows/s", "ms_per_step": ms4 / xs, "steps": xs, "result_check": chk4}
+    try:
+        ems4, _, _, _ = time_steps(ctx, torch, step4_e2e, xs, 3)
+        check_groupby(torch, state["cols4e"], kraw4, arrays4[1], 100_000, ["sum", "count"], "C4 e2e")
+        out["e2e_c4"] = {"value": total_rows * xs / (ems4 / 1e3), "unit": "rows/s", "h2d_bytes_per_step": 16 * n,
+                         "d2h_bytes_per_step": 24 * state["g4e"], "steps": xs, "ms_per_step": ems4 / xs,
+                         "path": "dfgpu_aggregate_update_host: pinned host batch -> chunked H2D overlapped with the scan kernel -> result columns to host"}
+    except AttributeError:
+        out["e2e_c4"] = None
+    b4.free()
+
+    try:
+        n5 = args.rows5 or (n * 5) // 4  # 1.25e8 rows per GPU: 8 GPUs = BASELINE's 1e9 rows
+        arrays5, keys5, aggs5, kraw5 = workloads.c5(n5, seed=46 + 10 * rank)
         b5 = ctx.upload(arrays5)
 
         def step5():
             r = ctx.aggregate(b5, keys5, aggs5)
             state["g5"] = r.nrows
+            if "keep5" in state:
+                state["cols5"] = r.columns()
             r.free()
         ms5, kms5, kn5, _ = time_steps(ctx, torch, step5, xs, 3)
+        state["keep5"] = True
+        step5()
+        chk5 = check_groupby(torch, state["cols5"], kraw5, arrays5[1], 1_000_000, ["min", "max", "sum"], "C5")
         k5 = kms5 / xs
-        extra["c5"] = {"workload": "C5-style: SELECT k, MIN(v), MAX(v), SUM(v) FROM t GROUP BY k; 1e6 Int64 keys, %d rows per GPU" % n
-                                   + (" + NCCL partial-aggregate merge" if world > 1 else ""),
-                       "groups": state["g5"], "value": total_rows * xs / (ms5 / 1e3), "unit": "rows/s", "ms_per_step": ms5 / xs, "kernel_ms": k5,
-                       "roofline": {"bound": "hbm", "achieved": bytes4 / (k5 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                    "frac": bytes4 / (k5 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes4, "kernel": "k_hash_agg"}}
+        bytes5 = 16.0 * n5
+        total5 = sum_over_ranks(torch, float(n5))
+        extra["c5"] = {"workload": "C5: SELECT k, MIN(v), MAX(v), SUM(v) FROM t GROUP BY k; 1e6 Int64 keys, %d rows per GPU (%.3g rows in all)%s"
+                                   % (n5, total5, merge),
+                       "groups": state["g5"], "value": total5 * xs / (ms5 / 1e3), "unit": "rows/s", "ms_per_step": ms5 / xs, "kernel_ms": k5,
+                       "roofline": {"bound": "hbm", "achieved": bytes5 / (k5 / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": bytes5 / (k5 / 1e3) / 1e9 / peak, "algorithmic_bytes": bytes5, "kernel": "k_hash_agg_plain"},
+                       "result_check": chk5}
         b5.free()
         del arrays5
+    except AssertionError:
+        raise
     except Exception as e:  # pragma: no cover
-        extra["c5" if "c4" in extra else "c4"] = {"error": repr(e)}
+        extra["c5"] = {"error": repr(e)}
     out["extra"] = extra
 
-    # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------
+    # ---- CPU baselines (rank 0, N=1 only) -----------------------------------------------------------
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(a, pred, proj, budget_s=12.0)
+        out["cpu_baseline_c4"] = cpu_baseline_c4(arrays4, keys4, aggs4)
     ctx.close()
     if rank == 0:
         print(json.dumps(out))
@@ -384,9 +485,23 @@ def cpu_baseline(a, pred, proj, budget_s):
                       "(README.md:20; Rc/RefCell operators are !Send)" % sample}
 
 
+def cpu_baseline_c4(arrays4, keys4, aggs4, sample=10_000_000):
+    """C4 through the oracle's with_group_by restatement (per-row key vector -> FNV map -> boxed accumulators,
+    aggregate.rs:787-952) on a stated prefix."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    sample = min(sample, len(arrays4[0]))
+    sub = [x[:sample] for x in arrays4]
+    t0 = time.perf_counter()
+    O.aggregate(sub, keys4, aggs4)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "rows/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "sample": "first %d rows of the C4 batch, one batch, one pass (%.1f s); single thread" % (sample, dt)}
+
+
 def run_reference(args):
-    """Reference arm: the CPU restatement of the reference's operators on the host cores."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    """Reference arm: the CPU restatement of the reference's operators on the host cores, same config as ours:
+    one full C2 batch (rows_per_gpu rows) per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -394,23 +509,27 @@ def run_reference(args):
     import oracle_lib as O
     from datafusion_archive_b200 import workloads
     n = args.rows
-    sample = min(n, args.ref_sample)
-    arrays, pred, proj = workloads.c2(sample, seed=42)
-    steps, warmup = args.steps, max(1, min(args.warmup, 3))
+    arrays, pred, proj = workloads.c2(n, seed=42)
+    steps, warmup = (args.steps or 5), max(3, args.warmup)
+    state = {}
     for _ in range(warmup):
-        O.filter_project(arrays, pred, proj)
+        state["out"] = O.filter_project(arrays, pred, proj)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.filter_project(arrays, pred, proj)
+        state["out"] = O.filter_project(arrays, pred, proj)
     dt = time.perf_counter() - t0
-    value = sample * steps / dt
+    n_sel = len(state["out"][0])
+    value = n * steps / dt
+    cfg = c2_config(n)
+    cfg["selectivity"] = n_sel / n
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: SELECT a FROM t WHERE a > 0.5; a~U[0,1) Float64, %d rows per GPU, seed 42+rank" % n, "rows_per_gpu": n},
+        "config": cfg,
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
-                         "sample": "each step = the first %d rows of the C2 batch through oracle/df_oracle.cpp (C++ restatement; the reference is "
-                                   "Rust and cannot be built in this image); 1 thread = the reference's execution model" % sample},
+                         "sample": "each step = the whole %d-row C2 batch through oracle/df_oracle.cpp (C++ restatement; the reference is "
+                                   "Rust and cannot be built in this image); 1 thread = the reference's execution model (README.md:20), "
+                                   "rank 0 only" % n},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -419,12 +538,12 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 2000 resident steps = ~0.6 s; reference arm: 5)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
-    ap.add_argument("--ref-sample", type=int, default=20_000_000, help="rows per step of the reference arm")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rows5", type=int, default=0, help="rows per GPU of the C5 extra (default 1.25 x --rows)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -107,6 +107,7 @@ struct AggParams {
   // the key / argument programs follow; rows that fail it are skipped before the probe
   int has_pred;
   int cond_mm;         // 1: MIN / MAX reductions are skipped when the value read with the probe already covers the row
+  int table_hint;      // 1: table loads / reductions carry an L2 evict-last policy
   PlainSpec plain;
 };
 
@@ -207,21 +208,48 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 }
 
 // One table line as read by a probe: word 0 = key, words 1..3 = the accumulators that share the line.
+// `pol` != 0: an L2 evict-last policy word — the table competes for L2 with a 1.6 GB input stream that is
+// read once (marked evict-first), so its lines should be the last to go.
 struct Line {
   unsigned long long w[4];
 };
 template <bool WITH_VALS>
-__device__ __forceinline__ void load_line(const TableLayout& t, long long slot, Line& ln) {
+__device__ __forceinline__ void load_line(const TableLayout& t, long long slot, Line& ln, unsigned long long pol = 0ull) {
   const unsigned long long* q = t.key(slot);
   if (WITH_VALS && t.lw >= 4) {  // 256-bit load (LDG.E.ENL2.256): lines are 32-byte aligned
-    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ln.w[0]), "=l"(ln.w[1]), "=l"(ln.w[2]), "=l"(ln.w[3]) : "l"(q) : "memory");
+    if (pol)
+      asm volatile("ld.global.cg.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(ln.w[0]), "=l"(ln.w[1]), "=l"(ln.w[2]), "=l"(ln.w[3]) : "l"(q), "l"(pol) : "memory");
+    else
+      asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ln.w[0]), "=l"(ln.w[1]), "=l"(ln.w[2]), "=l"(ln.w[3]) : "l"(q) : "memory");
   } else if (WITH_VALS && t.lw == 2) {
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(ln.w[0]), "=l"(ln.w[1]) : "l"(q) : "memory");
+    if (pol)
+      asm volatile("ld.global.cg.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(ln.w[0]), "=l"(ln.w[1]) : "l"(q), "l"(pol) : "memory");
+    else
+      asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(ln.w[0]), "=l"(ln.w[1]) : "l"(q) : "memory");
     ln.w[2] = ln.w[3] = 0ull;
   } else {
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(ln.w[0]) : "l"(q) : "memory");
+    if (pol)
+      asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(ln.w[0]) : "l"(q), "l"(pol) : "memory");
+    else
+      asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(ln.w[0]) : "l"(q) : "memory");
     ln.w[1] = ln.w[2] = ln.w[3] = 0ull;
   }
+}
+// fire-and-forget reductions with an L2 cache-policy operand
+__device__ __forceinline__ void red_add_f64(unsigned long long* p, double v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_f32(unsigned long long* p, float v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v, unsigned long long pol) {
+  asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_min_u64(unsigned long long* p, unsigned long long v, unsigned long long pol) {
+  asm volatile("red.global.min.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_max_u64(unsigned long long* p, unsigned long long v, unsigned long long pol) {
+  asm volatile("red.global.max.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ unsigned long long line_word(const Line& ln, int l) {
   return l == 1 ? ln.w[1] : (l == 2 ? ln.w[2] : ln.w[3]);
@@ -234,7 +262,7 @@ __device__ __forceinline__ unsigned long long line_word(const Line& ln, int l) {
 // probe limit): the row goes to the overflow list.
 template <bool WITH_VALS>
 __device__ __forceinline__ long long probe_insert(const TableLayout& t, long long cap, unsigned long long key, Line& ln,
-                                                  unsigned long long h, bool full, unsigned& new_groups) {
+                                                  unsigned long long h, bool full, unsigned& new_groups, unsigned long long pol = 0ull) {
   const unsigned long long mask = (unsigned long long)cap - 1ull;
   for (int probes = 0; probes < AG_MAX_PROBE; ++probes) {
     if (ln.w[0] == key) return (long long)h;
@@ -245,7 +273,7 @@ __device__ __forceinline__ long long probe_insert(const TableLayout& t, long lon
       if (old == key) return (long long)h;
     }
     h = (h + 1ull) & mask;
-    load_line<WITH_VALS>(t, (long long)h, ln);
+    load_line<WITH_VALS>(t, (long long)h, ln, pol);
   }
   return -1;
 }
@@ -253,17 +281,25 @@ __device__ __forceinline__ long long probe_insert(const TableLayout& t, long lon
 // fold one raw value into global memory; `cur` = the accumulator as read with the probe (have_cur): a
 // MIN / MAX that the row does not improve needs no reduction (the stored value only moves towards it)
 __device__ __forceinline__ void acc_fold_global_cond(int func, int mt, unsigned long long* p, unsigned long long v, bool have_cur,
-                                                     unsigned long long cur) {
+                                                     unsigned long long cur, unsigned long long pol) {
   if (func == DFGPU_AGG_MIN) {
     if (is_nan_val(v, mt)) return;
     const unsigned long long e = ord_enc(v, mt);
-    if (!have_cur || e < cur) atomicMin(p, e);
+    if (!have_cur || e < cur) { if (pol) red_min_u64(p, e, pol); else atomicMin(p, e); }
   } else if (func == DFGPU_AGG_MAX) {
     if (is_nan_val(v, mt)) return;
     const unsigned long long e = ord_enc(v, mt);
-    if (!have_cur || e > cur) atomicMax(p, e);
-  } else {
+    if (!have_cur || e > cur) { if (pol) red_max_u64(p, e, pol); else atomicMax(p, e); }
+  } else if (!pol) {
     acc_fold_global(func, mt, p, v);
+  } else if (func == DFGPU_AGG_COUNT) {
+    red_add_u64(p, 1ull, pol);
+  } else if (mt == MT_F64) {
+    red_add_f64(p, u2d(v), pol);
+  } else if (mt == MT_F32) {
+    red_add_f32(p, u2f(v), pol);
+  } else {
+    red_add_u64(p, v, pol);
   }
 }
 
@@ -299,10 +335,11 @@ constexpr int AG_FRONT_MAX_GROUPS = 1024;
 template <int DEPTH, bool NULLS>
 struct InterpSrc {
   static constexpr int R = AG_R;
+  static constexpr bool PREFETCH = false;
   GlobalRows<R> g;
   unsigned mask;  // rows to aggregate: in range and passing the predicate
   unsigned bad = 0;
-  __device__ __forceinline__ InterpSrc(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
+  __device__ __forceinline__ void load(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
     g.valid = 0;
     g.l2_policy = policy;
 #pragma unroll
@@ -312,6 +349,9 @@ struct InterpSrc {
       if (i < n) g.valid |= 1u << r;
     }
     mask = g.valid;
+    bad = 0;
+  }
+  __device__ __forceinline__ void prepare(const AggParams& p) {
     if (p.has_pred) {
       unsigned long long v[R];
       unsigned pv;
@@ -384,24 +424,35 @@ __device__ __forceinline__ unsigned cmp_bits2(int op, int mt, const unsigned lon
 #undef DF_C2
   return f;
 }
+// NC: column slots the instantiation holds (2 = the common key + value shape: fewer registers, more CTAs
+// per SM); PF: the loads of the NEXT tile are issued before the current tile's probes, so the HBM latency of
+// the input stream and the L2 latency of the probe chain overlap instead of adding up per thread.
+template <int NC, bool PF>
 struct PlainSrc {
   static constexpr int R = 2;
-  unsigned long long cv[4][2];
+  static constexpr bool PREFETCH = PF;
+  unsigned long long cv[NC][2];
   long long row0;
   unsigned mask;
   unsigned bad = 0;
   // value selects instead of indexed access: the column values stay in registers
   __device__ __forceinline__ void col(int s, unsigned long long (&v)[2]) const {
-    v[0] = s == 0 ? cv[0][0] : (s == 1 ? cv[1][0] : (s == 2 ? cv[2][0] : cv[3][0]));
-    v[1] = s == 0 ? cv[0][1] : (s == 1 ? cv[1][1] : (s == 2 ? cv[2][1] : cv[3][1]));
+    if (NC == 2) {
+      v[0] = s == 0 ? cv[0][0] : cv[1][0];
+      v[1] = s == 0 ? cv[0][1] : cv[1][1];
+    } else {
+      v[0] = s == 0 ? cv[0][0] : (s == 1 ? cv[1][0] : (s == 2 ? cv[2 % NC][0] : cv[3 % NC][0]));
+      v[1] = s == 0 ? cv[0][1] : (s == 1 ? cv[1][1] : (s == 2 ? cv[2 % NC][1] : cv[3 % NC][1]));
+    }
   }
-  __device__ __forceinline__ PlainSrc(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
+  __device__ __forceinline__ void load(const AggParams& p, long long tb, long long n, int tid, unsigned long long policy) {
     const long long i = tb + 2ll * tid;
     row0 = p.row_begin + i;  // even: tb and row_begin are even (host-checked)
     mask = (i < n ? 1u : 0u) | (i + 1 < n ? 2u : 0u);
+    bad = 0;
     const bool both = mask == 3u;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < NC; c++) {
       cv[c][0] = cv[c][1] = 0ull;
       if (c < p.plain.ncols && mask) {
         const int dt = p.ps.cols[c].dtype;  // warp-uniform
@@ -409,6 +460,8 @@ struct PlainSrc {
         else ld_pair32(p.ps.cols[c].ptr, row0, both, dt == DFGPU_INT32, cv[c]);
       }
     }
+  }
+  __device__ __forceinline__ void prepare(const AggParams& p) {
     if (p.plain.nterms > 0) {
       unsigned keep = 0;
       for (int t = 0; t < p.plain.nterms; t++) {
@@ -458,15 +511,22 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
   const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
   // the input is read exactly once: mark its lines evict-first so that they do not displace the table
   const unsigned long long stream_policy = p.stream_hint ? l2_evict_first_policy() : 0ull;
+  const unsigned long long tpol = p.table_hint ? l2_evict_last_policy() : 0ull;
   bool bad = false;
   constexpr int TILE = AG_THREADS * R;
-  for (long long tb = (long long)blockIdx.x * TILE; tb < n; tb += (long long)gridDim.x * TILE) {
+  const long long tstep = (long long)gridDim.x * TILE;
+  Src src, nxt;
+  bool first = true;
+  for (long long tb = (long long)blockIdx.x * TILE; tb < n; tb += tstep) {
     // fill limit, once per warp per tile (no CTA-wide barrier in the steady state)
     unsigned long long filled = 0;
     if (lane == 0) filled = __ldcg(&p.counters[0]);
     filled = __shfl_sync(0xffffffffu, filled, 0);
     const bool full = (long long)filled >= p.max_groups;
-    Src src(p, tb, n, tid, stream_policy);
+    if (!Src::PREFETCH || first) src.load(p, tb, n, tid, stream_policy);
+    first = false;
+    if (Src::PREFETCH && tb + tstep < n) nxt.load(p, tb + tstep, n, tid, stream_policy);
+    src.prepare(p);
     // group key: one packed 64-bit word (GroupByScalar vector of aggregate.rs:807-852)
     unsigned long long key[R];
 #pragma unroll
@@ -501,7 +561,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
       h[r] = mix64(key[r]) & hmask;
       probing[r] = ((src.mask >> r) & 1u) && key[r] != EMPTY_KEY && fslot[r] < 0;
       ln[r].w[0] = ln[r].w[1] = ln[r].w[2] = ln[r].w[3] = 0ull;
-      if (probing[r]) load_line<true>(p.t, (long long)h[r], ln[r]);
+      if (probing[r]) load_line<true>(p.t, (long long)h[r], ln[r], tpol);
     }
     long long slot[R];
     unsigned new_groups = 0;
@@ -514,7 +574,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
         slot[r] = p.cap;
         continue;
       }
-      slot[r] = probe_insert<true>(p.t, p.cap, key[r], ln[r], h[r], full, new_groups);
+      slot[r] = probe_insert<true>(p.t, p.cap, key[r], ln[r], h[r], full, new_groups, tpol);
       if (slot[r] < 0) {
         const unsigned long long at = atomicAdd(&p.counters[1], 1ull);
         p.ovf_rows[at] = src.rowid(r);
@@ -536,7 +596,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
             acc_fold_shared(func, mt, &ftab[(1 + a) * FS + fslot[r]], v[r]);
             if ((b >> r) & 1u) bad = true;
           } else if (slot[r] >= 0) {
-            acc_fold_global_cond(func, mt, p.t.val(slot[r], a), v[r], cond && probing[r], cond ? line_word(ln[r], l) : 0ull);
+            acc_fold_global_cond(func, mt, p.t.val(slot[r], a), v[r], cond && probing[r], cond ? line_word(ln[r], l) : 0ull, tpol);
             if ((b >> r) & 1u) bad = true;
           }
         }
@@ -547,6 +607,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
     if (lane == 0 && new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+    if (Src::PREFETCH) src = nxt;
   }
   if (FRONT) {
     // merge this CTA's front table into the global table.  New keys are always admitted here; the host
@@ -576,10 +637,10 @@ __global__ void __launch_bounds__(AG_THREADS) k_hash_agg(const __grid_constant__
   extern __shared__ unsigned long long s_front[];  // FRONT: keys[AG_FRONT_SLOTS] then vals[naggs][AG_FRONT_SLOTS]
   hash_agg_body<InterpSrc<DEPTH, NULLS>, FRONT, NULLS>(p, s_front);
 }
-template <bool FRONT>
-__global__ void __launch_bounds__(AG_THREADS) k_hash_agg_plain(const __grid_constant__ AggParams p) {
+template <int NC, bool PF, bool FRONT>
+__global__ void __launch_bounds__(AG_THREADS, 4) k_hash_agg_plain(const __grid_constant__ AggParams p) {
   extern __shared__ unsigned long long s_front[];
-  hash_agg_body<PlainSrc, FRONT, false>(p, s_front);
+  hash_agg_body<PlainSrc<NC, PF>, FRONT, false>(p, s_front);
 }
 
 // K4: no GROUP BY.  Per-thread accumulators live in shared memory (one 8-byte cell per thread per
@@ -752,6 +813,7 @@ struct CompactParams {
   long long cap;
   int sentinel_used;
   int nkeys, naggs, raw;
+  long long raw_stride;  // raw output: element idx of every raw array lives at idx * raw_stride (0 = 1: dense arrays)
   AggDesc aggs[kMaxAggs];
   // aggregates over the same argument expression (MIN(v), MAX(v), SUM(v)) share one evaluation:
   // programs [nkeys, nkeys + nargs) are the DISTINCT argument programs, agg_arg[a] picks one
@@ -784,8 +846,9 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
     if (!occ) continue;
     const long long idx = (long long)(basei + __popc(m & ((1u << lane) - 1u)));
     if (p.raw) {
-      ((unsigned long long*)p.out_keys[0])[idx] = key;
-      for (int a = 0; a < p.naggs; a++) ((unsigned long long*)p.out_vals[a])[idx] = *p.t.val(s, a);
+      const long long at = p.raw_stride ? idx * p.raw_stride : idx;
+      ((unsigned long long*)p.out_keys[0])[at] = key;
+      for (int a = 0; a < p.naggs; a++) ((unsigned long long*)p.out_vals[a])[at] = *p.t.val(s, a);
     } else {
       for (int k = 0; k < p.nkeys; k++) {
         unsigned long long v = (key >> p.key_shift[k]) & p.key_mask[k];
@@ -806,6 +869,7 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
 struct MergeParams {
   const unsigned long long* in_keys;
   const unsigned long long* in_vals[kMaxAggs];
+  long long in_stride;  // entry i of every input array lives at i * in_stride (0 = 1: dense arrays)
   long long n;
   TableLayout t;
   long long cap;
@@ -818,7 +882,8 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
   const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
   unsigned new_groups = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long key = p.in_keys[i];
+    const long long at = p.in_stride ? i * p.in_stride : i;
+    const unsigned long long key = p.in_keys[at];
     long long slot;
     if (key == EMPTY_KEY) {
       p.counters[2] = 1ull;
@@ -831,9 +896,75 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
       if (slot < 0) { p.counters[3] = 2ull; continue; }  // cannot happen: caller sizes the table
     }
     for (int a = 0; a < p.naggs; a++)
-      acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.t.val(slot, a), p.in_vals[a][i]);
+      acc_merge_global(p.aggs[a].func, p.aggs[a].mtype, p.t.val(slot, a), p.in_vals[a][at]);
   }
   if (new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+}
+
+// ---- owner-partitioned exchange of partial aggregates (multi-GPU merge) -----------------
+// Every group key has one OWNER rank, a function of the key alone, so that each rank merges only 1/W of the
+// keys: owner = bits of mix64(key) that the table slot does not use.
+constexpr int AG_MAX_WORLD = 64;
+__device__ __forceinline__ int owner_of(unsigned long long key, int world) {
+  return key == EMPTY_KEY ? 0 : (int)((mix64(key) >> 44) % (unsigned long long)world);
+}
+struct OwnerParams {
+  const unsigned long long* keys;              // raw (packed) keys of the local groups
+  const unsigned long long* vals[kMaxAggs];    // raw accumulators, dense arrays
+  long long n;
+  int world, naggs;
+  unsigned long long* counts;                  // [world] entries per owner
+  unsigned long long seg_off[AG_MAX_WORLD];    // scatter: first entry of owner o's segment in `rows`
+  unsigned long long* cursor;                  // [world], zeroed
+  unsigned long long* rows;                    // scatter output: entries of (1 + naggs) words, grouped by owner
+};
+__global__ void __launch_bounds__(256) k_owner_count(const __grid_constant__ OwnerParams p) {
+  __shared__ unsigned s_cnt[AG_MAX_WORLD];
+  if (threadIdx.x < AG_MAX_WORLD) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x)
+    atomicAdd(&s_cnt[owner_of(p.keys[i], p.world)], 1u);
+  __syncthreads();
+  if (threadIdx.x < p.world && s_cnt[threadIdx.x]) atomicAdd(&p.counts[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256) k_owner_scatter(const __grid_constant__ OwnerParams p) {
+  const long long E = 1 + p.naggs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = p.keys[i];
+    const int o = owner_of(key, p.world);
+    const unsigned long long j = p.seg_off[o] + atomicAdd(&p.cursor[o], 1ull);
+    unsigned long long* row = p.rows + j * E;
+    row[0] = key;
+    for (int a = 0; a < p.naggs; a++) row[1 + a] = p.vals[a][i];
+  }
+}
+
+// raw rows (key, accumulators...) -> typed result columns: group columns first, then aggregates
+// (aggregate.rs:890-949); the decode half of k_compact for rows that arrive from the exchange
+struct DecodeParams {
+  const unsigned long long* rows;
+  long long n;
+  int nkeys, naggs;
+  AggDesc aggs[kMaxAggs];
+  unsigned long long key_mask[kMaxKeys];
+  int key_shift[kMaxKeys];
+  int key_dtype[kMaxKeys];
+  void* out_keys[kMaxKeys];
+  void* out_vals[kMaxAggs];
+};
+__global__ void __launch_bounds__(256) k_decode_rows(const __grid_constant__ DecodeParams p) {
+  const long long E = 1 + p.naggs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long* row = p.rows + i * E;
+    const unsigned long long key = row[0];
+    for (int k = 0; k < p.nkeys; k++) store_elem(p.out_keys[k], p.key_dtype[k], i, (key >> p.key_shift[k]) & p.key_mask[k]);
+    for (int a = 0; a < p.naggs; a++) {
+      unsigned long long v = row[1 + a];
+      const int f = p.aggs[a].func;
+      if (f == DFGPU_AGG_MIN || f == DFGPU_AGG_MAX) v = ord_dec(v, p.aggs[a].mtype);
+      store_elem(p.out_vals[a], p.aggs[a].out_dtype, i, v);
+    }
+  }
 }
 
 // Utf8 GROUP BY keys are grouped by a 64-bit hash of the string; accumulator `rep_agg` holds the
@@ -974,7 +1105,7 @@ int grid_for(dfgpu_ctx* ctx, long long work_items, int per_block, int blocks_per
 
 // groups x (1 + naggs) sectors is what the SoA layout keeps hot in L2; beyond this many bytes the
 // table is built AoS (one sector per group).  B200 L2 = 126 MB, shared with the streaming input.
-constexpr long long AG_SOA_L2_BUDGET = 48ll << 20;
+constexpr long long AG_SOA_L2_BUDGET = 64ll << 20;
 
 // Cardinality estimate from a prefix sample: `d` distinct keys among the first `s` rows.  Under a
 // uniform model E[d] = G (1 - exp(-s / G)); solved for G by bisection and capped by the rows of the
@@ -1024,7 +1155,7 @@ bool want_aos(long long groups, const std::vector<AggDesc>& descs, int naggs) {
   signed char loc[kMaxAggs];
   layout_shape(descs, naggs, 1, false, &lw, &n_add, loc);
   const long long cap = std::max(AG_MIN_CAP, next_pow2(2 * groups));
-  const long long line_hot = groups * std::max<long long>(32, 8 * lw);
+  const long long line_hot = std::min(cap * 8 * lw, groups * std::max<long long>(32, 8 * lw));
   const long long arr_hot = std::min(cap * 8, groups * 32);
   return line_hot + n_add * arr_hot > AG_SOA_L2_BUDGET;
 }
@@ -1192,9 +1323,95 @@ extern "C" int dfgpu_aggregate_set_predicate(dfgpu_aggstate* st, const dfgpu_ins
   });
 }
 
+namespace {
+void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch);
+}
+
 extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
   return guarded([&] {
     if (!st || !batch) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_update: null argument");
+    agg_update(st, batch);
+  });
+}
+
+// One big host RecordBatch: row-range chunks, every H2D copy queued up front on the copy-in stream, the
+// scan of chunk c waits only for chunk c's copies — PCIe and the scan kernel overlap, and the table is
+// the only state carried from chunk to chunk (update_accumulators is per row: aggregate.rs:548-612).
+extern "C" int dfgpu_aggregate_update_host(dfgpu_aggstate* st, const dfgpu_col* cols, int ncols, int64_t chunk_rows) {
+  return guarded([&] {
+    if (!st || (ncols > 0 && !cols)) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_update_host: null argument");
+    dfgpu_ctx* ctx = st->ctx;
+    ctx->use();
+    const int64_t n = ncols > 0 ? cols[0].len : 0;
+    bool streamable = n > 0;
+    for (int i = 0; i < ncols; i++) {
+      if (cols[i].len != n) fail(DFGPU_ERR_GENERAL, "all columns of a RecordBatch must have the same length");
+      streamable = streamable && dtype_width(cols[i].dtype) > 0 && !cols[i].validity && cols[i].values;
+    }
+    if (chunk_rows <= 0) chunk_rows = 8ll << 20;
+    chunk_rows = (chunk_rows + 1023) / 1024 * 1024;  // chunks start on even, 16-byte aligned rows of every column
+    if (!streamable || n <= chunk_rows) {
+      // small, nullable or variable-width batches: plain upload (Utf8 / validity handling lives there)
+      dfgpu_batch* b = nullptr;
+      int rc = dfgpu_batch_upload(ctx, cols, ncols, &b);
+      if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+      struct G { dfgpu_batch* b; ~G() { dfgpu_batch_free(b); } } g{b};
+      agg_update(st, b);
+      return;
+    }
+    const int nchunks = int((n + chunk_rows - 1) / chunk_rows);
+    std::vector<void*> dev(size_t(ncols), nullptr);
+    std::vector<cudaEvent_t> evs(size_t(nchunks), nullptr);
+    struct Cleanup {
+      dfgpu_ctx* c; std::vector<void*>* d; std::vector<cudaEvent_t>* e;
+      ~Cleanup() {
+        cudaStreamSynchronize(c->stream_in);
+        cudaStreamSynchronize(c->stream);
+        for (void* q : *d) c->free(q);
+        for (cudaEvent_t x : *e) if (x) cudaEventDestroy(x);
+      }
+    } cleanup{ctx, &dev, &evs};
+    for (int i = 0; i < ncols; i++) dev[size_t(i)] = ctx->alloc(size_t(n) * size_t(dtype_width(cols[i].dtype)));
+    // the device buffers may have been used on ctx->stream before (cached blocks): order the copies after it
+    cudaEvent_t ready;
+    DF_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    DF_CUDA(cudaEventRecord(ready, ctx->stream));
+    DF_CUDA(cudaStreamWaitEvent(ctx->stream_in, ready, 0));
+    DF_CUDA(cudaEventDestroy(ready));
+    for (int c = 0; c < nchunks; c++) {
+      const int64_t lo = int64_t(c) * chunk_rows, cnt = std::min<int64_t>(chunk_rows, n - lo);
+      for (int i = 0; i < ncols; i++) {
+        const size_t w = size_t(dtype_width(cols[i].dtype));
+        DF_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(dev[size_t(i)]) + size_t(lo) * w,
+                                static_cast<const uint8_t*>(cols[i].values) + size_t(cols[i].offset + lo) * w, size_t(cnt) * w,
+                                cudaMemcpyHostToDevice, ctx->stream_in));
+      }
+      DF_CUDA(cudaEventCreateWithFlags(&evs[size_t(c)], cudaEventDisableTiming));
+      DF_CUDA(cudaEventRecord(evs[size_t(c)], ctx->stream_in));
+    }
+    for (int c = 0; c < nchunks; c++) {
+      const int64_t lo = int64_t(c) * chunk_rows, cnt = std::min<int64_t>(chunk_rows, n - lo);
+      DF_CUDA(cudaStreamWaitEvent(ctx->stream, evs[size_t(c)], 0));
+      dfgpu_batch view;  // borrows the chunk's slices of the device buffers
+      view.ctx = ctx;
+      view.owns = false;
+      view.nrows = cnt;
+      for (int i = 0; i < ncols; i++) {
+        DevColumn d;
+        d.dtype = cols[i].dtype;
+        const size_t w = size_t(dtype_width(cols[i].dtype));
+        d.values = static_cast<uint8_t*>(dev[size_t(i)]) + size_t(lo) * w;
+        d.values_bytes = size_t(cnt) * w;
+        view.cols.push_back(d);
+      }
+      agg_update(st, &view);
+    }
+  });
+}
+
+namespace {
+void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
+  {
     if (st->finished) fail(DFGPU_ERR_GENERAL, "aggregate already finished");
     dfgpu_ctx* ctx = st->ctx;
     ctx->use();
@@ -1344,6 +1561,8 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
     {
       static const bool no_cond = getenv("DFGPU_AGG_COND_MM") && atoi(getenv("DFGPU_AGG_COND_MM")) == 0;  // A/B switch
       p.cond_mm = no_cond ? 0 : 1;
+      static const bool hint = getenv("DFGPU_AGG_TABLE_HINT") && atoi(getenv("DFGPU_AGG_TABLE_HINT")) != 0;  // A/B switch (default off until measured)
+      p.table_hint = hint ? 1 : 0;
     }
     const int d = p.ps.max_depth;
 
@@ -1499,8 +1718,18 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
         // went from 1.57 to 7.8 ms at 1e5 groups and from 3.4 to 15 ms at 1e6, profiles/r02a_l2persist.txt.)
         if (p.ps.has_nulls) launch_scan(ctx, k_hash_agg<8, false, true>, p, n, false);
         else if (use_plain && !list && (p.row_begin & 1) == 0) {
-          if (front) launch_scan(ctx, k_hash_agg_plain<true>, p, n, true);
-          else launch_scan(ctx, k_hash_agg_plain<false>, p, n, false);
+          static const bool no_pf = getenv("DFGPU_AGG_PREFETCH") && atoi(getenv("DFGPU_AGG_PREFETCH")) == 0;  // A/B switch
+          const bool two = p.plain.ncols <= 2;
+          if (front) {
+            if (two) launch_scan(ctx, k_hash_agg_plain<2, false, true>, p, n, true);
+            else launch_scan(ctx, k_hash_agg_plain<4, false, true>, p, n, true);
+          } else if (no_pf) {
+            if (two) launch_scan(ctx, k_hash_agg_plain<2, false, false>, p, n, false);
+            else launch_scan(ctx, k_hash_agg_plain<4, false, false>, p, n, false);
+          } else {
+            if (two) launch_scan(ctx, k_hash_agg_plain<2, true, false>, p, n, false);
+            else launch_scan(ctx, k_hash_agg_plain<4, true, false>, p, n, false);
+          }
         } else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
         else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
         else if (d <= 4) launch_hash_agg<4>(ctx, p, n, front);
@@ -1561,44 +1790,26 @@ extern "C" int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* bat
       if (ctx->h_scratch[12] == 1ull) fail(DFGPU_ERR_INTERNAL, "two different Utf8 GROUP BY keys share a 64-bit hash (p < 1e-7 per 1e6 distinct keys)");
       if (ctx->h_scratch[12]) fail(DFGPU_ERR_INTERNAL, "Utf8 GROUP BY verification could not find a group");
     }
-  });
-}
-
-// Exchange hooks used by the communicator (api.cu): raw compaction of the local table and merge of
-// remote entries.  Declared here, defined below.
-namespace dfgpu {
-void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n);
-void agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n, long long val_stride);
-void agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st);
-int agg_naggs(const dfgpu_aggstate* st) { return st->naggs; }
-// api.cu (NCCL)
-void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
-                       unsigned long long* d_vals, unsigned long long* d_nonnull);
-}  // namespace dfgpu
-
-void dfgpu::agg_exchange(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
-  int funcs[kMaxAggs], mtypes[kMaxAggs];
-  for (int a = 0; a < st->naggs; a++) {
-    funcs[a] = st->descs[size_t(a)].func;
-    mtypes[a] = st->descs[size_t(a)].mtype;
   }
-  if (st->nkeys == 0) {
-    // per-aggregate non-null input counts travel with the accumulators: fold the host-side counts of the
-    // null-free batches into the device counters, which the exchange sums over ranks
-    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 40, st->d_counters + 8, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    DF_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int a = 0; a < kMaxAggs; a++) {
-      if (a < st->naggs) ctx->h_scratch[40 + a] += (unsigned long long)st->nonnull_host[size_t(a)];
-      if (a < st->naggs) st->nonnull_host[size_t(a)] = 0;
-    }
-    DF_CUDA(cudaMemcpyAsync(st->d_counters + 8, ctx->h_scratch + 40, 64, cudaMemcpyHostToDevice, ctx->stream));
-    st->saw_nulls = true;
-  }
-  agg_exchange_impl(ctx, st, &st->rows_seen, st->nkeys, funcs, mtypes, st->t.val(0, 0),  // no GROUP BY: slot 0's accumulators (cap = 0, SoA: contiguous)
-                    st->d_counters + 8);
 }
+}  // namespace
 
-void dfgpu::agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n) {
+// ---------------------------------------------------------------------------------------------
+// multi-GPU merge of partial aggregates.  Every rank ends with the global result.
+//   no GROUP BY : one ncclAllReduce per accumulator (api.cu comm_allreduce_aggs)
+//   GROUP BY    : open-addressed slots are not canonical across ranks, so the all-reduce is sparse and
+//                 owner-partitioned:  raw-compact the local table -> count entries per owner rank ->
+//                 all-gather a (header, counts) record -> scatter the entries into per-owner segments ->
+//                 ONE grouped ncclSend/ncclRecv all-to-all -> each rank merges only the keys it owns into a
+//                 fresh table (k_merge) -> compacts them -> all ranks gather the owned segments
+//                 (grouped ncclBroadcast) and decode the same rows in the same order, so results are
+//                 bit-identical on every rank.  Work per rank is O(G_local + G/W + G), not O(W x G).
+// A rank that never saw a batch takes part with zero entries and adopts the key / argument types of a rank
+// that did (they travel in the header).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n) {
   dfgpu_ctx* ctx = st->ctx;
   const long long cnt = st->nkeys == 0 ? 1 : st->ngroups + (st->sentinel_used ? 1 : 0);
   const size_t alloc_n = size_t(cnt > 0 ? cnt : 1);
@@ -1625,32 +1836,227 @@ void dfgpu::agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsign
   *n = cnt;
 }
 
-void dfgpu::agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n,
-                          long long val_stride) {
-  dfgpu_ctx* ctx = st->ctx;
-  if (n <= 0) return;
-  if (st->nkeys > 0 && (st->ngroups + n) * 2 > st->cap) table_grow(st, next_pow2((st->ngroups + n) * 4));
-  MergeParams mp;
-  memset(&mp, 0, sizeof(mp));
-  mp.in_keys = keys;
+// no GROUP BY
+void agg_exchange_scalars(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
+  int funcs[kMaxAggs], mtypes[kMaxAggs];
   for (int a = 0; a < st->naggs; a++) {
-    mp.in_vals[a] = vals + size_t(a) * size_t(val_stride);
-    mp.aggs[a] = st->descs[size_t(a)];
+    funcs[a] = st->descs[size_t(a)].func;
+    mtypes[a] = st->descs[size_t(a)].mtype;
   }
-  mp.n = n;
-  mp.t = st->t;
-  mp.cap = st->cap;
-  mp.naggs = st->naggs;
-  mp.counters = st->d_counters;
-  k_merge<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(mp);
-  DF_CUDA(cudaGetLastError());
-  ctx->launches++;
-  unsigned long long c[8];
-  read_counters(st, c);
-  if (c[3]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed");
-  st->ngroups = (long long)c[0];
-  st->sentinel_used = c[2] != 0;
+  // per-aggregate non-null input counts travel with the accumulators: fold the host-side counts of the
+  // null-free batches into the device counters, which the exchange sums over ranks
+  DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 40, st->d_counters + 8, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int a = 0; a < kMaxAggs; a++) {
+    if (a < st->naggs) ctx->h_scratch[40 + a] += (unsigned long long)st->nonnull_host[size_t(a)];
+    if (a < st->naggs) st->nonnull_host[size_t(a)] = 0;
+  }
+  ctx->h_scratch[48] = (unsigned long long)st->rows_seen;
+  DF_CUDA(cudaMemcpyAsync(st->d_counters + 8, ctx->h_scratch + 40, 64, cudaMemcpyHostToDevice, ctx->stream));
+  DF_CUDA(cudaMemcpyAsync(st->d_counters + 7, ctx->h_scratch + 48, 8, cudaMemcpyHostToDevice, ctx->stream));
+  st->saw_nulls = true;
+  // slot 0's accumulators (cap = 0: every accumulator in its own one-word array, contiguous)
+  comm_allreduce_aggs(ctx, st->naggs, funcs, mtypes, st->t.val(0, 0), st->d_counters + 8, st->d_counters + 7);
+  DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 48, st->d_counters + 7, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  st->rows_seen = (long long)ctx->h_scratch[48];
 }
+
+// GROUP BY.  Returns the global result as raw rows of (1 + naggs) words in *rows (caller frees) and their number.
+constexpr int HDR = 16;  // header words: [0] typed [1] nkeys [2] naggs [3] utf8 [4] rows_seen [5] key dtypes (8 bits each) [6] arg dtypes (8 bits each)
+void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long** rows_out, long long* n_out) {
+  const int W = ctx->world, me = ctx->rank;
+  if (W > AG_MAX_WORLD) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than " + std::to_string(AG_MAX_WORLD) + " ranks");
+  Trace tr(ctx);
+  std::vector<void*> owned;
+  struct Freer { dfgpu_ctx* c; std::vector<void*>* v; ~Freer() { for (void* q : *v) c->free(q); } } freer{ctx, &owned};
+  auto dalloc = [&](size_t words) { void* q = ctx->alloc((words ? words : 1) * 8); owned.push_back(q); return (unsigned long long*)q; };
+  // 1. local entries, counted per owner
+  unsigned long long *keys = nullptr, *vals = nullptr;
+  long long n_local = 0;
+  if (st->typed) {
+    agg_export_raw(st, &keys, &vals, &n_local);
+    owned.push_back(keys);
+    owned.push_back(vals);
+  }
+  unsigned long long* d_rec = dalloc(size_t(HDR + W));
+  DF_CUDA(cudaMemsetAsync(d_rec, 0, size_t(HDR + W) * 8, ctx->stream));
+  OwnerParams op;
+  memset(&op, 0, sizeof(op));
+  op.keys = keys;
+  const size_t ln = size_t(n_local > 0 ? n_local : 1);
+  for (int a = 0; a < st->naggs; a++) op.vals[a] = vals + size_t(a) * ln;
+  op.n = n_local;
+  op.world = W;
+  op.naggs = st->naggs;
+  op.counts = d_rec + HDR;
+  if (n_local > 0) {
+    k_owner_count<<<grid_for(ctx, n_local, 256 * 4, 8), 256, 0, ctx->stream>>>(op);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  unsigned long long* hh = ctx->h_scratch + 16;  // pinned
+  memset(hh, 0, HDR * 8);
+  hh[0] = st->typed ? 1 : 0;
+  hh[1] = (unsigned long long)st->nkeys;
+  hh[2] = (unsigned long long)st->naggs;
+  hh[3] = st->utf8_key ? 1 : 0;
+  hh[4] = (unsigned long long)st->rows_seen;
+  if (st->typed) {
+    for (int k = 0; k < st->nkeys; k++) hh[5] |= (unsigned long long)(st->key_dtypes[size_t(k)] & 0xff) << (8 * k);
+    for (int a = 0; a < st->naggs; a++) hh[6] |= (unsigned long long)(st->descs[size_t(a)].dtype & 0xff) << (8 * a);
+  }
+  DF_CUDA(cudaMemcpyAsync(d_rec, hh, HDR * 8, cudaMemcpyHostToDevice, ctx->stream));
+  // 2. all-gather (header, counts)
+  unsigned long long* d_all = dalloc(size_t(W) * size_t(HDR + W));
+  comm_allgather_u64(ctx, d_rec, d_all, size_t(HDR + W));
+  std::vector<unsigned long long> all(size_t(W) * size_t(HDR + W));
+  DF_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  auto hdr = [&](int r, int i) { return all[size_t(r) * size_t(HDR + W) + size_t(i)]; };
+  auto cnt = [&](int from, int to) { return (size_t)all[size_t(from) * size_t(HDR + W) + size_t(HDR + to)]; };
+  // 3. agree on types; adopt them on a rank that saw no batch
+  int typed_rank = -1;
+  long long total_rows = 0;
+  for (int r = 0; r < W; r++) {
+    total_rows += (long long)hdr(r, 4);
+    if ((int)hdr(r, 1) != st->nkeys) fail(DFGPU_ERR_GENERAL, "ranks disagree on the GROUP BY expressions");
+    if (hdr(r, 3)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys with a multi-GPU communicator");
+    if (hdr(r, 0)) {
+      if (typed_rank < 0) typed_rank = r;
+      else if (hdr(r, 5) != hdr(typed_rank, 5) || hdr(r, 6) != hdr(typed_rank, 6) || hdr(r, 2) != hdr(typed_rank, 2))
+        fail(DFGPU_ERR_GENERAL, "ranks disagree on GROUP BY key / aggregate argument types");
+    }
+  }
+  st->rows_seen = total_rows;
+  if (!st->typed) {
+    st->key_dtypes.clear();
+    st->descs.clear();
+    for (int k = 0; k < st->nkeys; k++) st->key_dtypes.push_back(typed_rank >= 0 ? int((hdr(typed_rank, 5) >> (8 * k)) & 0xff) : DFGPU_INT64);
+    for (int a = 0; a < st->naggs; a++) {
+      int dt = typed_rank >= 0 ? int((hdr(typed_rank, 6) >> (8 * a)) & 0xff) : st->out_dtypes[size_t(a)];
+      if (!is_numeric(dt)) dt = DFGPU_FLOAT64;
+      AggDesc d;
+      d.func = uint8_t(st->funcs[size_t(a)]);
+      d.dtype = uint8_t(dt);
+      d.mtype = mtype_of(dt);
+      d.out_dtype = uint8_t(d.func == DFGPU_AGG_COUNT ? DFGPU_UINT64 : dt);
+      st->descs.push_back(d);
+    }
+    st->key_shift.clear();
+    st->key_mask.clear();
+    int bits = 0;
+    for (int k = st->nkeys - 1; k >= 0; k--) {
+      const int w = dtype_width(st->key_dtypes[size_t(k)]) * 8;
+      st->key_shift.insert(st->key_shift.begin(), bits);
+      st->key_mask.insert(st->key_mask.begin(), w == 64 ? ~0ull : ((1ull << w) - 1ull));
+      bits += w;
+    }
+    if (st->nkeys == 1) st->key_mask[0] = ~0ull;
+    st->typed = true;
+  }
+  const size_t E = size_t(1 + st->naggs);
+  // 4. scatter the local entries into per-owner segments
+  std::vector<size_t> s_off(size_t(W), 0), s_cnt(size_t(W), 0), r_off(size_t(W), 0), r_cnt(size_t(W), 0);
+  size_t total_send = 0, total_recv = 0;
+  for (int r = 0; r < W; r++) {
+    s_off[size_t(r)] = total_send * E;
+    s_cnt[size_t(r)] = cnt(me, r) * E;
+    total_send += cnt(me, r);
+    r_off[size_t(r)] = total_recv * E;
+    r_cnt[size_t(r)] = cnt(r, me) * E;
+    total_recv += cnt(r, me);
+  }
+  if ((long long)total_send != n_local) fail(DFGPU_ERR_INTERNAL, "owner counts do not add up to the local groups");
+  unsigned long long* d_send = dalloc(total_send * E);
+  if (n_local > 0) {
+    unsigned long long* d_cursor = dalloc(size_t(W));
+    DF_CUDA(cudaMemsetAsync(d_cursor, 0, size_t(W) * 8, ctx->stream));
+    op.cursor = d_cursor;
+    op.rows = d_send;
+    for (int r = 0; r < W; r++) op.seg_off[r] = s_off[size_t(r)] / E;
+    k_owner_scatter<<<grid_for(ctx, n_local, 256 * 4, 8), 256, 0, ctx->stream>>>(op);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  // 5. all-to-all: every entry goes to its owner
+  unsigned long long* d_recv = dalloc(total_recv * E);
+  comm_exchange_v(ctx, d_send, s_off.data(), s_cnt.data(), d_recv, r_off.data(), r_cnt.data());
+  tr.mark("exchange: export + all-to-all");
+  // 6. merge what this rank owns into a fresh table
+  long long n_owned = 0;
+  unsigned long long* d_owned = nullptr;
+  if (total_recv > 0) {
+    const long long ocap = std::max<long long>(1024, next_pow2(2 * (long long)total_recv));
+    const bool oaos = want_aos((long long)total_recv, st->descs, st->naggs);
+    TableLayout ot = table_alloc(ctx, st->naggs, st->nkeys, st->descs, ocap, oaos);
+    owned.push_back(ot.base);
+    MergeParams mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.in_keys = d_recv;
+    for (int a = 0; a < st->naggs; a++) {
+      mp.in_vals[a] = d_recv + 1 + a;
+      mp.aggs[a] = st->descs[size_t(a)];
+    }
+    mp.in_stride = (long long)E;
+    mp.n = (long long)total_recv;
+    mp.t = ot;
+    mp.cap = ocap;
+    mp.naggs = st->naggs;
+    DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 32, ctx->stream));
+    mp.counters = st->d_counters;
+    k_merge<<<grid_for(ctx, mp.n, 256, 8), 256, 0, ctx->stream>>>(mp);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+    unsigned long long c[8];
+    read_counters(st, c);
+    if (c[3]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed");
+    n_owned = (long long)c[0] + (c[2] ? 1 : 0);
+    d_owned = dalloc(size_t(n_owned) * E);
+    CompactParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.t = ot;
+    cp.cap = ocap;
+    cp.sentinel_used = c[2] ? 1 : 0;
+    cp.nkeys = st->nkeys;
+    cp.naggs = st->naggs;
+    cp.raw = 1;
+    cp.raw_stride = (long long)E;
+    cp.out_keys[0] = d_owned;
+    for (int a = 0; a < st->naggs; a++) {
+      cp.aggs[a] = st->descs[size_t(a)];
+      cp.out_vals[a] = d_owned + 1 + a;
+    }
+    DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
+    cp.counter = st->d_counters + 4;
+    k_compact<<<grid_for(ctx, ocap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
+    DF_CUDA(cudaGetLastError());
+    ctx->launches++;
+  }
+  // 7. every rank gathers the owned segments (sizes first)
+  unsigned long long* d_n = dalloc(size_t(1 + W));
+  ctx->h_scratch[16] = (unsigned long long)n_owned;
+  DF_CUDA(cudaMemcpyAsync(d_n, ctx->h_scratch + 16, 8, cudaMemcpyHostToDevice, ctx->stream));
+  comm_allgather_u64(ctx, d_n, d_n + 1, 1);
+  std::vector<unsigned long long> owned_n(size_t(W), 0);
+  DF_CUDA(cudaMemcpyAsync(owned_n.data(), d_n + 1, size_t(W) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<size_t> g_off(size_t(W), 0), g_cnt(size_t(W), 0);
+  size_t G = 0;
+  for (int r = 0; r < W; r++) {
+    g_off[size_t(r)] = G * E;
+    g_cnt[size_t(r)] = size_t(owned_n[size_t(r)]) * E;
+    G += size_t(owned_n[size_t(r)]);
+  }
+  unsigned long long* d_final = (unsigned long long*)ctx->alloc((G ? G * E : 1) * 8);
+  comm_allgather_v(ctx, d_owned, d_final, g_off.data(), g_cnt.data());
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));  // the temporaries above are released on return
+  tr.mark("exchange: owner merge + gather");
+  *rows_out = d_final;
+  *n_out = (long long)G;
+}
+
+}  // namespace
 
 extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
   return guarded([&] {
@@ -1659,7 +2065,7 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     dfgpu_ctx* ctx = st->ctx;
     ctx->use();
     Trace tr(ctx);
-    if (!st->typed) {
+    if (!st->typed && !(st->nkeys > 0 && ctx->world > 1)) {
       // no batch was ever seen: resolve types from the declared output types
       if (st->nkeys > 0) {
         // an empty GROUP BY input yields an empty batch; key types are unknown -> need a batch
@@ -1679,13 +2085,17 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       st->cap = 0;
       st->t = table_alloc(ctx, st->naggs, st->nkeys, st->descs, 0, false);
     }
+    // multi-GPU: every rank must take part (also one that saw no batch), and every rank gets the global result
+    unsigned long long* xrows = nullptr;
+    long long xn = -1;
+    struct XFree { dfgpu_ctx* c; unsigned long long** p; ~XFree() { c->free(*p); } } xfree{ctx, &xrows};
     if (ctx->world > 1) {
-      // every rank must take part, and ranks reduce row counts too (null-ness of the global result)
-      agg_exchange(ctx, st);
+      if (st->nkeys == 0) agg_exchange_scalars(ctx, st);
+      else agg_exchange_groups(ctx, st, &xrows, &xn);
     }
     auto res = std::make_unique<dfgpu_result>();
     res->ctx = ctx;
-    const long long cnt = st->nkeys == 0 ? 1 : st->ngroups + (st->sentinel_used ? 1 : 0);
+    const long long cnt = xn >= 0 ? xn : (st->nkeys == 0 ? 1 : st->ngroups + (st->sentinel_used ? 1 : 0));
     const size_t alloc_n = size_t(cnt > 0 ? cnt : 1);
     CompactParams cp;
     memset(&cp, 0, sizeof(cp));
@@ -1725,14 +2135,40 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       cp.out_vals[a] = c.values;
       cp.aggs[a] = st->descs[size_t(a)];
     }
-    DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
-    cp.counter = st->d_counters + 4;
-    k_compact<<<grid_for(ctx, st->cap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
-    DF_CUDA(cudaGetLastError());
-    ctx->launches++;
-    DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    DF_CUDA(cudaStreamSynchronize(ctx->stream));
-    if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
+    if (xn >= 0) {
+      // the merged global rows came back from the exchange: decode them (same rows, same order on every rank)
+      DecodeParams dp;
+      memset(&dp, 0, sizeof(dp));
+      dp.rows = xrows;
+      dp.n = xn;
+      dp.nkeys = st->nkeys;
+      dp.naggs = st->naggs;
+      for (int k = 0; k < st->nkeys; k++) {
+        dp.key_mask[k] = cp.key_mask[k];
+        dp.key_shift[k] = cp.key_shift[k];
+        dp.key_dtype[k] = cp.key_dtype[k];
+        dp.out_keys[k] = cp.out_keys[k];
+      }
+      for (int a = 0; a < st->naggs; a++) {
+        dp.aggs[a] = cp.aggs[a];
+        dp.out_vals[a] = cp.out_vals[a];
+      }
+      if (xn > 0) {
+        k_decode_rows<<<grid_for(ctx, xn, 256, 8), 256, 0, ctx->stream>>>(dp);
+        DF_CUDA(cudaGetLastError());
+        ctx->launches++;
+      }
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+      DF_CUDA(cudaMemsetAsync(st->d_counters + 4, 0, 8, ctx->stream));
+      cp.counter = st->d_counters + 4;
+      k_compact<<<grid_for(ctx, st->cap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
+      DF_CUDA(cudaGetLastError());
+      ctx->launches++;
+      DF_CUDA(cudaMemcpyAsync(ctx->h_scratch + 8, st->d_counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));
+      if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
+    }
     res->nrows = cnt;
     if (st->utf8_key)  // key strings = the representatives' strings, in output order
       gather_utf8_multi(ctx, st->d_utf8_srcs, (const unsigned long long*)hidden.cols[1].values, cnt, &res->cols[0]);

@@ -164,7 +164,7 @@ extern "C" int dfgpu_profile_get(dfgpu_ctx* ctx, double* kernel_ms, int64_t* lau
 }
 
 dfgpu_batch::~dfgpu_batch() {
-  if (!ctx) return;
+  if (!ctx || !owns) return;
   cudaSetDevice(ctx->device);
   for (auto& c : cols) {
     ctx->free(c.values);
@@ -545,6 +545,9 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -562,6 +565,7 @@ NcclApi& nccl() {
   *(void**)(&api.N) = dlsym(h, "nccl" #N);                          \
   if (!api.N) fail(DFGPU_ERR_CUDA, "libnccl is missing symbol nccl" #N);
   LOAD(GetUniqueId) LOAD(CommInitRank) LOAD(CommDestroy) LOAD(AllGather) LOAD(AllReduce) LOAD(GroupStart) LOAD(GroupEnd)
+  LOAD(Send) LOAD(Recv) LOAD(Broadcast)
   LOAD(GetErrorString)
 #undef LOAD
   api.h = h;
@@ -602,6 +606,11 @@ extern "C" int dfgpu_comm_init(dfgpu_ctx* ctx, int rank, int world, const uint8_
   });
 }
 
+extern "C" int dfgpu_comm_world(const dfgpu_ctx* ctx, int64_t* world) {
+  *world = ctx ? ctx->world : 1;
+  return 0;
+}
+
 extern "C" int dfgpu_comm_destroy(dfgpu_ctx* ctx) {
   return guarded([&] {
     if (ctx && ctx->nccl_comm) {
@@ -617,86 +626,73 @@ extern "C" int dfgpu_comm_destroy(dfgpu_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// partial-aggregate merge across ranks.  Every rank ends with the global result
-// (all-reduce semantics).  No GROUP BY: a true ncclAllReduce per accumulator (SUM -> ncclSum,
-// COUNT -> ncclSum, MIN/MAX -> ncclMin/ncclMax on the order-preserving u64 encoding).  GROUP BY:
-// a sparse all-reduce = ncclAllGather of the compacted (key, accumulators) lists + a local merge
-// kernel (aggregate.cu: k_merge), because open-addressed slots are not canonical across ranks.
+// Collectives used by the partial-aggregate merge (aggregate.cu: agg_exchange_groups).
+// All traffic is u64 words on ctx->stream; counts / offsets are in words.
+//   comm_allgather_u64 : fixed-size all-gather (headers, counts)
+//   comm_exchange_v    : personalised all-to-all — one grouped ncclSend / ncclRecv pair per peer (the
+//                        owner-partitioned exchange of partial aggregates); the self segment is copied locally
+//   comm_allgather_v   : every rank's final segment to every rank (one grouped ncclBroadcast per root)
+//   comm_allreduce_aggs: no-GROUP-BY accumulators: one ncclAllReduce each (ncclSum on f64/u64, ncclMin/ncclMax
+//                        on the order-preserving u64 encoding)
 // ---------------------------------------------------------------------------------------------
-struct dfgpu_aggstate;
 namespace dfgpu {
-void agg_export_raw(dfgpu_aggstate* st, unsigned long long** keys, unsigned long long** vals, long long* n);
-void agg_merge_raw(dfgpu_aggstate* st, const unsigned long long* keys, const unsigned long long* vals, long long n, long long val_stride);
-int agg_naggs(const dfgpu_aggstate* st);
-void agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs, const int* mtypes,
-                       unsigned long long* d_vals, unsigned long long* d_nonnull);
-}  // namespace dfgpu
 
-void dfgpu::agg_exchange_impl(dfgpu_ctx* ctx, dfgpu_aggstate* st, long long* rows_seen, int nkeys, const int* funcs,
-                              const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull) {
-  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-  if (!comm) fail(DFGPU_ERR_GENERAL, "world > 1 but no communicator");
-  const int W = ctx->world, naggs = agg_naggs(st);
-  NcclApi& N = nccl();
-  // counts: [n_local, rows_seen] per rank
-  unsigned long long* d_cnt = (unsigned long long*)ctx->alloc(size_t(2 * (W + 1)) * 8);
-  unsigned long long *keys = nullptr, *vals = nullptr;
-  long long n_local = 0;
-  if (nkeys > 0) agg_export_raw(st, &keys, &vals, &n_local);
-  ctx->h_scratch[16] = (unsigned long long)n_local;
-  ctx->h_scratch[17] = (unsigned long long)*rows_seen;
-  DF_CUDA(cudaMemcpyAsync(d_cnt, ctx->h_scratch + 16, 16, cudaMemcpyHostToDevice, ctx->stream));
-  DF_NCCL(N.AllGather(d_cnt, d_cnt + 2, 2, ncclUint64, comm, ctx->stream));
-  std::vector<unsigned long long> cnt(size_t(2 * W));
-  DF_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt + 2, size_t(2 * W) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  DF_CUDA(cudaStreamSynchronize(ctx->stream));
-  ctx->free(d_cnt);
-  long long total_rows = 0, max_n = 0;
-  for (int r = 0; r < W; r++) {
-    total_rows += (long long)cnt[size_t(2 * r + 1)];
-    max_n = std::max(max_n, (long long)cnt[size_t(2 * r)]);
-  }
-  *rows_seen = total_rows;
-  if (nkeys == 0) {
-    DF_NCCL(N.GroupStart());
-    for (int a = 0; a < naggs; a++) {
-      ncclDataType_t dt = ncclUint64;
-      ncclRedOp_t op = ncclSum;
-      if (funcs[a] == DFGPU_AGG_MIN) op = ncclMin;
-      else if (funcs[a] == DFGPU_AGG_MAX) op = ncclMax;
-      else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 1 /*MT_F64*/) dt = ncclFloat64;
-      else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 2 /*MT_F32*/) dt = ncclFloat32;
-      // f32 accumulators occupy the low 4 bytes of their 8-byte cell
-      DF_NCCL(N.AllReduce(d_vals + a, d_vals + a, 1, dt, op, comm, ctx->stream));
-    }
-    // non-null input counts per aggregate (an aggregate that saw none anywhere is null)
-    DF_NCCL(N.AllReduce(d_nonnull, d_nonnull, 8, ncclUint64, ncclSum, comm, ctx->stream));
-    DF_NCCL(N.GroupEnd());
-    DF_CUDA(cudaStreamSynchronize(ctx->stream));
-    return;
-  }
-  // payload: per rank (1 + naggs) arrays of max_n u64
-  const size_t per_rank = size_t(1 + naggs) * size_t(max_n);
-  if (max_n > 0) {
-    unsigned long long* send = (unsigned long long*)ctx->alloc(per_rank * 8);
-    unsigned long long* recv = (unsigned long long*)ctx->alloc(per_rank * 8 * size_t(W));
-    const size_t ln = size_t(n_local > 0 ? n_local : 1);
-    if (n_local > 0) {
-      DF_CUDA(cudaMemcpyAsync(send, keys, size_t(n_local) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-      for (int a = 0; a < naggs; a++)
-        DF_CUDA(cudaMemcpyAsync(send + size_t(1 + a) * size_t(max_n), vals + size_t(a) * ln, size_t(n_local) * 8,
-                                cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-    DF_NCCL(N.AllGather(send, recv, per_rank, ncclUint64, comm, ctx->stream));
-    for (int r = 0; r < W; r++) {
-      if (r == ctx->rank) continue;
-      const unsigned long long* base = recv + size_t(r) * per_rank;
-      agg_merge_raw(st, base, base + size_t(max_n), (long long)cnt[size_t(2 * r)], max_n);
-    }
-    DF_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->free(send);
-    ctx->free(recv);
-  }
-  ctx->free(keys);
-  ctx->free(vals);
+static ncclComm_t comm_of(dfgpu_ctx* ctx) {
+  if (!ctx->nccl_comm) fail(DFGPU_ERR_GENERAL, "world > 1 but no communicator");
+  return (ncclComm_t)ctx->nccl_comm;
 }
+
+void comm_allgather_u64(dfgpu_ctx* ctx, const unsigned long long* send, unsigned long long* recv, size_t count) {
+  DF_NCCL(nccl().AllGather(send, recv, count, ncclUint64, comm_of(ctx), ctx->stream));
+}
+
+void comm_exchange_v(dfgpu_ctx* ctx, const unsigned long long* send, const size_t* send_off, const size_t* send_cnt,
+                     unsigned long long* recv, const size_t* recv_off, const size_t* recv_cnt) {
+  NcclApi& N = nccl();
+  ncclComm_t comm = comm_of(ctx);
+  const int W = ctx->world, me = ctx->rank;
+  if (send_cnt[me])
+    DF_CUDA(cudaMemcpyAsync(recv + recv_off[me], send + send_off[me], send_cnt[me] * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  DF_NCCL(N.GroupStart());
+  for (int r = 0; r < W; r++) {
+    if (r == me) continue;
+    if (send_cnt[r]) DF_NCCL(N.Send(send + send_off[r], send_cnt[r], ncclUint64, r, comm, ctx->stream));
+    if (recv_cnt[r]) DF_NCCL(N.Recv(recv + recv_off[r], recv_cnt[r], ncclUint64, r, comm, ctx->stream));
+  }
+  DF_NCCL(N.GroupEnd());
+}
+
+void comm_allgather_v(dfgpu_ctx* ctx, const unsigned long long* send, unsigned long long* recv, const size_t* off, const size_t* cnt) {
+  NcclApi& N = nccl();
+  ncclComm_t comm = comm_of(ctx);
+  const int W = ctx->world, me = ctx->rank;
+  DF_NCCL(N.GroupStart());
+  for (int r = 0; r < W; r++) {
+    if (!cnt[r]) continue;
+    DF_NCCL(N.Broadcast(r == me ? (const void*)send : (const void*)(recv + off[r]), recv + off[r], cnt[r], ncclUint64, r, comm, ctx->stream));
+  }
+  DF_NCCL(N.GroupEnd());
+}
+
+void comm_allreduce_aggs(dfgpu_ctx* ctx, int naggs, const int* funcs, const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull,
+                         unsigned long long* d_rows /* [1] rows seen, summed */) {
+  NcclApi& N = nccl();
+  ncclComm_t comm = comm_of(ctx);
+  DF_NCCL(N.GroupStart());
+  for (int a = 0; a < naggs; a++) {
+    ncclDataType_t dt = ncclUint64;
+    ncclRedOp_t op = ncclSum;
+    if (funcs[a] == DFGPU_AGG_MIN) op = ncclMin;
+    else if (funcs[a] == DFGPU_AGG_MAX) op = ncclMax;
+    else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 1 /*MT_F64*/) dt = ncclFloat64;
+    else if (funcs[a] == DFGPU_AGG_SUM && mtypes[a] == 2 /*MT_F32*/) dt = ncclFloat32;
+    // f32 accumulators occupy the low 4 bytes of their 8-byte cell
+    DF_NCCL(N.AllReduce(d_vals + a, d_vals + a, 1, dt, op, comm, ctx->stream));
+  }
+  // non-null input counts per aggregate (an aggregate that saw none anywhere is null) and the row count
+  DF_NCCL(N.AllReduce(d_nonnull, d_nonnull, 8, ncclUint64, ncclSum, comm, ctx->stream));
+  DF_NCCL(N.AllReduce(d_rows, d_rows, 1, ncclUint64, ncclSum, comm, ctx->stream));
+  DF_NCCL(N.GroupEnd());
+}
+
+}  // namespace dfgpu

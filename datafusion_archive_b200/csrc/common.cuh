@@ -130,6 +130,13 @@ struct DevColumn {
 };
 
 namespace dfgpu {
+// collectives over the ctx's NCCL communicator (api.cu); counts and offsets in u64 words, all on ctx->stream
+void comm_allgather_u64(dfgpu_ctx* ctx, const unsigned long long* send, unsigned long long* recv, size_t count);
+void comm_exchange_v(dfgpu_ctx* ctx, const unsigned long long* send, const size_t* send_off, const size_t* send_cnt,
+                     unsigned long long* recv, const size_t* recv_off, const size_t* recv_cnt);
+void comm_allgather_v(dfgpu_ctx* ctx, const unsigned long long* send, unsigned long long* recv, const size_t* off, const size_t* cnt);
+void comm_allreduce_aggs(dfgpu_ctx* ctx, int naggs, const int* funcs, const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull,
+                         unsigned long long* d_rows);
 // one Utf8 column on the device (arrow 0.12 BinaryArray): the unit of the multi-source string gather
 struct Utf8Source {
   const int* off;
@@ -142,6 +149,7 @@ struct dfgpu_batch {
   dfgpu_ctx* ctx = nullptr;
   int64_t nrows = 0;
   std::vector<DevColumn> cols;
+  bool owns = true;  // false: a view into buffers owned elsewhere (chunks of dfgpu_aggregate_update_host)
   ~dfgpu_batch();  // returns the column buffers to the ctx pool
 };
 

@@ -122,6 +122,9 @@ int dfhost_context_new(int device, dfhost_context** out) {
 }
 void dfhost_context_free(dfhost_context* c) { delete c; }
 int dfhost_context_set_verbose(dfhost_context* c, int on) { c->ctx->verbose = on != 0; return 0; }
+int dfhost_context_set_partition(dfhost_context* c, int rank, int world, const uint8_t* nccl_unique_id) {
+  return guarded([&] { c->ctx->set_partition(rank, world, nccl_unique_id); });
+}
 
 int dfhost_register_csv(dfhost_context* c, const char* table, const char* filename, int ncols, const char* const* names,
                         const int32_t* dtypes, int64_t batch_size) {

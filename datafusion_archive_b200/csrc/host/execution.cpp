@@ -370,24 +370,58 @@ GpuFilterProjectRelation::GpuFilterProjectRelation(dfgpu_ctx* gpu, RelationRef i
 std::optional<RecordBatch> GpuFilterProjectRelation::next() {
   auto batch = input_->next();
   if (!batch) return std::nullopt;
+  // proj_ empty: FilterRelation alone gathers every input column (filter.rs:55-57).
+  std::vector<ExprRef> exprs = proj_;
+  if (exprs.empty())
+    for (size_t c = 0; c < batch->columns.size(); c++) exprs.push_back(Expr::column(c));
+  // One kernel pass takes a bounded number of distinct columns and expressions (kMaxCols / kMaxProgs of
+  // expr_vm.cuh), so a wide select list is evaluated in several passes over groups of expressions; every pass
+  // evaluates the same predicate and therefore keeps the same rows in the same order.
+  constexpr size_t kCols = 12, kProgs = 23;
+  std::set<size_t> pcols;
+  if (predicate_) collect_columns(*predicate_, pcols);
+  std::vector<std::vector<size_t>> groups(1);
+  std::set<size_t> used = pcols;
+  for (size_t i = 0; i < exprs.size(); i++) {
+    std::set<size_t> with = used;
+    collect_columns(*exprs[i], with);
+    if (!groups.back().empty() && (with.size() > kCols || groups.back().size() >= kProgs)) {
+      groups.emplace_back();
+      with = pcols;
+      collect_columns(*exprs[i], with);
+    }
+    used = with;
+    groups.back().push_back(i);
+  }
+  if (groups.size() == 1) return process(*batch, exprs, schema_);
+  RecordBatch out;
+  out.schema = schema_;
+  for (auto& g : groups) {
+    std::vector<ExprRef> part_exprs;
+    auto sub = std::make_shared<Schema>();
+    for (size_t i : g) {
+      part_exprs.push_back(exprs[i]);
+      sub->fields.push_back(schema_->fields[i]);
+    }
+    RecordBatch part = process(*batch, part_exprs, sub);
+    out.num_rows = part.num_rows;
+    for (auto& col : part.columns) out.columns.push_back(col);
+  }
+  return out;
+}
+
+RecordBatch GpuFilterProjectRelation::process(const RecordBatch& in_batch, const std::vector<ExprRef>& proj, const SchemaRef& out_schema) {
+  const RecordBatch* batch = &in_batch;
   const Schema& in_schema = *input_->schema();
-  std::vector<ExprRef> all = proj_;
+  std::vector<ExprRef> all = proj;
   all.push_back(predicate_);
-  const bool emit_all = proj_.empty();  // FilterRelation alone gathers every input column (filter.rs:55-57)
-  Pruned pr = prune(all, batch->columns.size(), emit_all);
+  Pruned pr = prune(all, batch->columns.size(), false);
   std::vector<dfgpu_insn> pred;
   if (predicate_) lower(*predicate_, in_schema, pr.remap, pred);
   std::vector<std::vector<dfgpu_insn>> progs;
-  if (emit_all) {
-    for (size_t c = 0; c < batch->columns.size(); c++) {
-      progs.emplace_back();
-      lower(*Expr::column(c), in_schema, pr.remap, progs.back());
-    }
-  } else {
-    for (auto& e : proj_) {
-      progs.emplace_back();
-      lower(*e, in_schema, pr.remap, progs.back());
-    }
+  for (auto& e : proj) {
+    progs.emplace_back();
+    lower(*e, in_schema, pr.remap, progs.back());
   }
   std::vector<const dfgpu_insn*> pp;
   std::vector<int> pl;
@@ -397,7 +431,7 @@ std::optional<RecordBatch> GpuFilterProjectRelation::next() {
   // zero-copy (the pinned block lives as long as the RecordBatch).
   bool numeric_only = batch->num_rows >= (4ll << 20);
   for (size_t c : pr.cols) numeric_only = numeric_only && datatype_width(batch->columns[c]->data_type) > 0 && batch->columns[c]->null_count == 0;
-  for (auto& f : schema_->fields) numeric_only = numeric_only && datatype_width(f.data_type) > 0;  // Boolean / Utf8 outputs: resident path
+  for (auto& f : out_schema->fields) numeric_only = numeric_only && datatype_width(f.data_type) > 0;  // Boolean / Utf8 outputs: resident path
   if (numeric_only) {
     std::vector<dfgpu_col> cols;
     for (size_t c : pr.cols) cols.push_back(batch->columns[c]->view());
@@ -405,7 +439,7 @@ std::optional<RecordBatch> GpuFilterProjectRelation::next() {
     GPU_CHECK(dfgpu_filter_project_host(gpu_, cols.data(), int(cols.size()), pred.data(), int(pred.size()), pp.data(), pl.data(), int(pp.size()), 0, &raw));
     std::shared_ptr<void> owner(raw, [](void* p) { dfgpu_result_free(static_cast<dfgpu_result*>(p)); });
     RecordBatch out;
-    out.schema = schema_;
+    out.schema = out_schema;
     int64_t nrows = 0;
     int ncols = 0;
     GPU_CHECK(dfgpu_result_shape(raw, &nrows, &ncols));
@@ -429,12 +463,38 @@ std::optional<RecordBatch> GpuFilterProjectRelation::next() {
   b.b = upload(gpu_, *batch, pr);
   ResultGuard r;
   GPU_CHECK(dfgpu_filter_project(gpu_, b.b, pred.data(), int(pred.size()), pp.data(), pl.data(), int(pp.size()), &r.r));
-  return download(r.r, schema_);
+  return download(r.r, out_schema);
 }
 
 GpuAggregateRelation::GpuAggregateRelation(dfgpu_ctx* gpu, SchemaRef schema, RelationRef input, std::vector<ExprRef> group_expr,
-                                           std::vector<ExprRef> aggr_expr)
-    : gpu_(gpu), schema_(std::move(schema)), input_(std::move(input)), group_expr_(std::move(group_expr)), aggr_expr_(std::move(aggr_expr)) {}
+                                           std::vector<ExprRef> aggr_expr, ExprRef predicate)
+    : gpu_(gpu), schema_(std::move(schema)), input_(std::move(input)), group_expr_(std::move(group_expr)), aggr_expr_(std::move(aggr_expr)),
+      predicate_(std::move(predicate)) {}
+
+std::optional<RecordBatch> ShardRelation::next() {
+  auto batch = input_->next();
+  if (!batch) return std::nullopt;
+  const int64_t n = batch->num_rows, per = (n + world_ - 1) / world_;
+  const int64_t lo = std::min<int64_t>(n, int64_t(rank_) * per), hi = std::min<int64_t>(n, lo + per);
+  RecordBatch out;
+  out.schema = batch->schema;
+  out.num_rows = hi - lo;
+  for (auto& c : batch->columns) {
+    auto s = std::make_shared<Array>(*c);  // shares the buffers
+    s->offset = c->offset + lo;
+    s->len = hi - lo;
+    if (c->null_count > 0 && c->validity) {
+      int64_t nulls = 0;
+      for (int64_t r = 0; r < s->len; r++) nulls += !((c->validity[(s->offset + r) >> 3] >> ((s->offset + r) & 7)) & 1);
+      s->null_count = nulls;
+    }
+    if (!c->own_values.empty()) { s->values = s->own_values.data(); }
+    if (!c->own_validity.empty()) { s->validity = s->own_validity.data(); }
+    if (!c->own_offsets.empty()) { s->offsets = s->own_offsets.data(); }
+    out.columns.push_back(s);
+  }
+  return out;
+}
 
 std::optional<RecordBatch> GpuAggregateRelation::next() {
   if (end_of_results_) return std::nullopt;  // aggregate.rs:616-619
@@ -452,6 +512,7 @@ std::optional<RecordBatch> GpuAggregateRelation::next() {
     funcs.push_back(f);
     all.push_back(a->args[0]);
   }
+  if (predicate_) all.push_back(predicate_);
   dfgpu_aggstate* st = nullptr;
   struct StGuard { dfgpu_aggstate** s; ~StGuard() { if (*s) dfgpu_aggregate_free(*s); } } sg{&st};
   std::optional<Pruned> pr;
@@ -476,13 +537,50 @@ std::optional<RecordBatch> GpuAggregateRelation::next() {
         aggs[a]._pad = 0;
       }
       GPU_CHECK(dfgpu_aggregate_create(gpu_, kptr.data(), klen.data(), int(kptr.size()), aggs.data(), int(aggs.size()), 0, &st));
+      if (predicate_) {  // Aggregate{input: Selection}: the WHERE clause runs inside the scan kernel
+        std::vector<dfgpu_insn> pred;
+        lower(*predicate_, in_schema, pr->remap, pred);
+        GPU_CHECK(dfgpu_aggregate_set_predicate(st, pred.data(), int(pred.size())));
+      }
     }
-    BatchGuard b;
-    b.b = upload(gpu_, *batch, *pr);
-    GPU_CHECK(dfgpu_aggregate_update(st, b.b));
+    // host buffers straight in: large batches are uploaded in chunks that overlap with the scan
+    std::vector<dfgpu_col> cols;
+    for (size_t c : pr->cols) cols.push_back(batch->columns[c]->view());
+    if (cols.empty()) fail(DFGPU_ERR_NOT_IMPLEMENTED, "queries that reference no column");
+    GPU_CHECK(dfgpu_aggregate_update_host(st, cols.data(), int(cols.size()), 0));
   }
   if (!st) {
-    // empty input: no GROUP BY -> one row of nulls; GROUP BY -> empty batch
+    // empty input: no GROUP BY -> one row of nulls; GROUP BY -> empty batch (with a communicator attached the
+    // rank still has to join the exchange: an empty aggregate state does that)
+    int64_t world = 1;
+    dfgpu_comm_world(gpu_, &world);
+    if (!group_expr_.empty() && world > 1) {
+      const Schema& isch = in_schema;
+      std::vector<ExprRef> ex = group_expr_;
+      for (auto& a : aggr_expr_) ex.push_back(a->args[0]);
+      Pruned p0 = prune(ex, isch.fields.size(), false);
+      std::vector<std::vector<dfgpu_insn>> kp(group_expr_.size()), ap(aggr_expr_.size());
+      std::vector<const dfgpu_insn*> kptr;
+      std::vector<int> klen;
+      for (size_t k = 0; k < group_expr_.size(); k++) {
+        lower(*group_expr_[k], isch, p0.remap, kp[k]);
+        kptr.push_back(kp[k].data());
+        klen.push_back(int(kp[k].size()));
+      }
+      std::vector<dfgpu_agg> aggs(aggr_expr_.size());
+      for (size_t a = 0; a < aggr_expr_.size(); a++) {
+        lower(*aggr_expr_[a]->args[0], isch, p0.remap, ap[a]);
+        aggs[a].func = funcs[a];
+        aggs[a].arg = ap[a].data();
+        aggs[a].arg_len = int(ap[a].size());
+        aggs[a].out_dtype = aggr_expr_[a]->data_type;
+        aggs[a]._pad = 0;
+      }
+      GPU_CHECK(dfgpu_aggregate_create(gpu_, kptr.data(), klen.data(), int(kptr.size()), aggs.data(), int(aggs.size()), 0, &st));
+      ResultGuard r;
+      GPU_CHECK(dfgpu_aggregate_finish(st, &r.r));
+      return download(r.r, schema_);
+    }
     if (!group_expr_.empty()) {
       RecordBatch out;
       out.schema = schema_;
@@ -529,6 +627,12 @@ ExecutionContext::~ExecutionContext() {
   if (gpu_) dfgpu_shutdown(gpu_);
 }
 
+void ExecutionContext::set_partition(int rank, int world, const uint8_t* nccl_unique_id) {
+  GPU_CHECK(dfgpu_comm_init(gpu_, rank, world, nccl_unique_id));
+  rank_ = rank;
+  world_ = world;
+}
+
 void ExecutionContext::register_datasource(const std::string& name, DataSourceRef ds) { (*datasources_)[name] = std::move(ds); }
 
 PlanRef ExecutionContext::plan(const std::string& sql) {
@@ -546,7 +650,9 @@ RelationRef ExecutionContext::execute(const PlanRef& plan) {
     case LogicalPlan::TableScan: {
       auto it = datasources_->find(plan->table_name);
       if (it == datasources_->end()) fail(DFGPU_ERR_GENERAL, "No table registered as '" + plan->table_name + "'");
-      return std::make_shared<DataSourceRelation>(it->second);
+      RelationRef scan = std::make_shared<DataSourceRelation>(it->second);
+      if (world_ > 1) return std::make_shared<ShardRelation>(scan, rank_, world_);  // this rank's row range of every batch
+      return scan;
     }
     case LogicalPlan::Selection: {  // context.rs:126-139 -> FilterRelation
       RelationRef input_rel = execute(plan->input);
@@ -567,8 +673,17 @@ RelationRef ExecutionContext::execute(const PlanRef& plan) {
       return std::make_shared<GpuFilterProjectRelation>(gpu_, input_rel, pred, plan->expr, schema);
     }
     case LogicalPlan::Aggregate: {  // context.rs:162-192 -> AggregateRelation
-      RelationRef input_rel = execute(plan->input);
-      return std::make_shared<GpuAggregateRelation>(gpu_, plan->schema(), input_rel, plan->group_expr, plan->aggr_expr);
+      // Aggregate{input: Selection{expr, input}} (what `SELECT .. WHERE .. GROUP BY ..` plans to,
+      // sqlplanner.rs:93-96): the reference stacks FilterRelation under AggregateRelation; here the predicate is
+      // handed to the aggregate's scan kernel and only the columns it, the keys and the arguments read are uploaded
+      ExprRef pred;
+      PlanRef src = plan->input;
+      if (src->kind == LogicalPlan::Selection) {
+        pred = src->expr[0];
+        src = src->input;
+      }
+      RelationRef input_rel = execute(src);
+      return std::make_shared<GpuAggregateRelation>(gpu_, plan->schema(), input_rel, plan->group_expr, plan->aggr_expr, pred);
     }
     default:
       fail(DFGPU_ERR_NOT_IMPLEMENTED, "Limit / Sort / EmptyRelation plans are not executable (reference: unimplemented!() at context.rs:194)");

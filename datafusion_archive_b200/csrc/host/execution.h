@@ -96,6 +96,7 @@ class GpuFilterProjectRelation : public Relation {
   std::optional<RecordBatch> next() override;
   const SchemaRef& schema() const override { return schema_; }
  private:
+  RecordBatch process(const RecordBatch& batch, const std::vector<ExprRef>& proj, const SchemaRef& out_schema);
   dfgpu_ctx* gpu_;
   RelationRef input_;
   ExprRef predicate_;
@@ -103,10 +104,26 @@ class GpuFilterProjectRelation : public Relation {
   SchemaRef schema_;
 };
 
-// AggregateRelation: src/execution/aggregate.rs:38-61, 615-631
+// Row-range shard of a relation for one-process-per-GPU execution: rank g of G passes on rows
+// [g*ceil(n/G), min(n, (g+1)*ceil(n/G))) of every batch (zero copy: Array offset / len).  Inserted above the
+// TableScan by ExecutionContext::execute when a partition is set.
+class ShardRelation : public Relation {
+ public:
+  ShardRelation(RelationRef input, int rank, int world) : input_(std::move(input)), rank_(rank), world_(world) {}
+  std::optional<RecordBatch> next() override;
+  const SchemaRef& schema() const override { return input_->schema(); }
+ private:
+  RelationRef input_;
+  int rank_, world_;
+};
+
+// AggregateRelation: src/execution/aggregate.rs:38-61, 615-631.  `predicate` (may be null) is the expression
+// of a Selection directly under the Aggregate (context.rs:126-139 builds FilterRelation there): it is fused
+// into the scan kernel instead of materialising the filtered batch.
 class GpuAggregateRelation : public Relation {
  public:
-  GpuAggregateRelation(dfgpu_ctx* gpu, SchemaRef schema, RelationRef input, std::vector<ExprRef> group_expr, std::vector<ExprRef> aggr_expr);
+  GpuAggregateRelation(dfgpu_ctx* gpu, SchemaRef schema, RelationRef input, std::vector<ExprRef> group_expr, std::vector<ExprRef> aggr_expr,
+                       ExprRef predicate = nullptr);
   std::optional<RecordBatch> next() override;
   const SchemaRef& schema() const override { return schema_; }
  private:
@@ -114,6 +131,7 @@ class GpuAggregateRelation : public Relation {
   SchemaRef schema_;
   RelationRef input_;
   std::vector<ExprRef> group_expr_, aggr_expr_;
+  ExprRef predicate_;
   bool end_of_results_ = false;
 };
 
@@ -126,10 +144,19 @@ class ExecutionContext {
   RelationRef execute(const PlanRef& plan);                                   // context.rs:104-196
   PlanRef plan(const std::string& sql);                                       // parse + plan only
   dfgpu_ctx* gpu() const { return gpu_; }
+  // One process (ExecutionContext) per GPU: attach this context to an NCCL communicator and make it work on
+  // its row range of every table.  Aggregates then return the GLOBAL result on every rank (partial-aggregate
+  // merge inside dfgpu_aggregate_finish); filter / project relations return this rank's rows, and the
+  // rank-ordered concatenation of all ranks' outputs is the global output.  `nccl_unique_id`: 128 bytes from
+  // dfgpu_comm_unique_id on rank 0.
+  void set_partition(int rank, int world, const uint8_t* nccl_unique_id);
+  int rank() const { return rank_; }
+  int world() const { return world_; }
   bool verbose = false;  // the reference prints "Logical plan: ..." on every execute (context.rs:105)
  private:
   std::shared_ptr<std::map<std::string, DataSourceRef>> datasources_;
   dfgpu_ctx* gpu_ = nullptr;
+  int rank_ = 0, world_ = 1;
 };
 
 // Expr name as RuntimeExpr::get_name reports it (expression.rs:230,312,322,407)

@@ -71,6 +71,7 @@ def lib():
     L.dfgpu_aggregate_create.argtypes = [vp, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(A.Agg), C.c_int, C.c_int64, C.POINTER(vp)]
     L.dfgpu_aggregate_set_predicate.argtypes = [vp, PI, C.c_int]
     L.dfgpu_aggregate_update.argtypes = [vp, vp]
+    L.dfgpu_aggregate_update_host.argtypes = [vp, C.POINTER(A.Col), C.c_int, C.c_int64]
     L.dfgpu_aggregate_finish.argtypes = [vp, C.POINTER(vp)]
     L.dfgpu_aggregate_free.argtypes = [vp]
     L.dfgpu_result_shape.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
@@ -278,6 +279,27 @@ class GpuContext:
                 check(lib().dfgpu_aggregate_set_predicate(st, parr, len(pprog)))
             for b in batches:
                 check(lib().dfgpu_aggregate_update(st, b.h))
+            out = C.c_void_p()
+            check(lib().dfgpu_aggregate_finish(st, C.byref(out)))
+            return Result(self, out)
+        finally:
+            lib().dfgpu_aggregate_free(st)
+
+    def aggregate_host(self, arrays, keys=(), aggs=(), expected_groups=0, pred=None, chunk_rows=0):
+        """AggregateRelation over one big HOST batch: chunked H2D overlapped with the scan inside the library."""
+        keep = []
+        cols = A.make_cols(arrays, keep)
+        schema = [cols[i].dtype for i in range(len(arrays))]
+        kptrs, klens, nk = A.make_programs([k.program(schema) for k in keys], keep)
+        aggarr = A.make_aggs([a.lower(schema) for a in aggs], keep)
+        st = C.c_void_p()
+        check(lib().dfgpu_aggregate_create(self.h, kptrs, klens, nk, aggarr, len(aggs), expected_groups, C.byref(st)))
+        try:
+            if pred is not None:
+                pprog = pred.program(schema)
+                parr = (A.Insn * max(1, len(pprog)))(*pprog)
+                check(lib().dfgpu_aggregate_set_predicate(st, parr, len(pprog)))
+            check(lib().dfgpu_aggregate_update_host(st, cols, len(arrays), chunk_rows))
             out = C.c_void_p()
             check(lib().dfgpu_aggregate_finish(st, C.byref(out)))
             return Result(self, out)

@@ -56,6 +56,7 @@ def lib():
         L.dfhost_context_new.argtypes = [C.c_int, C.POINTER(vp)]
         L.dfhost_context_free.argtypes = [vp]
         L.dfhost_context_set_verbose.argtypes = [vp, C.c_int]
+        L.dfhost_context_set_partition.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
         L.dfhost_register_csv.argtypes = [vp, cp, cp, C.c_int, C.POINTER(cp), C.POINTER(C.c_int32), C.c_int64]
         L.dfhost_register_memory.argtypes = [vp, cp, C.c_int, C.POINTER(cp), C.POINTER(A.Col), C.c_int64]
         L.dfhost_sql.argtypes = [vp, cp, C.POINTER(vp)]
@@ -239,6 +240,11 @@ class ExecutionContext:
         names = (C.c_char_p * len(arrays))(*[n.encode() for n, _ in named_arrays])
         self._keep.append(cols)
         _check(lib().dfhost_register_memory(self.h, table.encode(), len(arrays), names, cols, batch_size))
+
+    def set_partition(self, rank, world, unique_id):
+        """One process per GPU: join the NCCL communicator (unique_id from engine.comm_unique_id() on rank 0)
+        and work on this rank's row range of every table; aggregates return the global result on every rank."""
+        _check(lib().dfhost_context_set_partition(self.h, rank, world, unique_id))
 
     def sql(self, sql):
         out = C.c_void_p()

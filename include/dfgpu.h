@@ -209,6 +209,11 @@ int dfgpu_aggregate_create(dfgpu_ctx* ctx, const dfgpu_insn* const* keys, const 
  * first dfgpu_aggregate_update; pred_len == 0 removes it. */
 int dfgpu_aggregate_set_predicate(dfgpu_aggstate* st, const dfgpu_insn* pred, int pred_len);
 int dfgpu_aggregate_update(dfgpu_aggstate* st, const dfgpu_batch* batch);
+/* Same as update for one big HOST RecordBatch (the `while let Some(batch)` body with the upload inside): the
+ * batch is cut into row-range chunks, every H2D copy is queued up front on a copy stream and the scan of
+ * chunk c waits only for chunk c's copies, so PCIe and the kernel overlap.  Input buffers should be pinned
+ * (dfgpu_host_alloc).  Nullable / Utf8 / small batches take the plain upload path inside. */
+int dfgpu_aggregate_update_host(dfgpu_aggstate* st, const dfgpu_col* cols, int ncols, int64_t chunk_rows /*0 = default*/);
 int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out);
 int dfgpu_aggregate_free(dfgpu_aggstate* st);
 
@@ -236,6 +241,8 @@ int dfgpu_result_free(dfgpu_result* r);
 int dfgpu_comm_unique_id(uint8_t out_id[128]);
 int dfgpu_comm_init(dfgpu_ctx* ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
 int dfgpu_comm_destroy(dfgpu_ctx* ctx);
+/* Number of ranks of the attached communicator (1 = none). */
+int dfgpu_comm_world(const dfgpu_ctx* ctx, int64_t* world);
 
 #ifdef __cplusplus
 }

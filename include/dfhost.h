@@ -50,6 +50,9 @@ void dfhost_datasource_free(dfhost_datasource* d);
 int dfhost_context_new(int device, dfhost_context** out);
 void dfhost_context_free(dfhost_context* c);
 int dfhost_context_set_verbose(dfhost_context* c, int on); /* the reference's `println!("Logical plan: ..")` */
+/* one process per GPU: join an NCCL communicator (128-byte id from dfgpu_comm_unique_id on rank 0) and work on
+ * this rank's row range of every table; aggregates return the global result on every rank */
+int dfhost_context_set_partition(dfhost_context* c, int rank, int world, const uint8_t* nccl_unique_id);
 int dfhost_register_csv(dfhost_context* c, const char* table, const char* filename, int ncols, const char* const* names,
                         const int32_t* dtypes, int64_t batch_size);
 /* in-memory table over borrowed Arrow buffers (must outlive the relation), sliced into batch_size rows */

@@ -1,9 +1,13 @@
 """Worker for the world_size>1 tests (launched by torch.distributed.run).
-  mode gloo : CPU.  Each rank computes its shard with the ORACLE (test infrastructure), partials are
-              exchanged over gloo, merged with parallel.merge_partials, checked against the oracle on
-              the full data.  Exercises the partitioning + merge algebra without a GPU.
+  mode gloo : CPU.  A numpy MODEL of the multi-GPU protocol (datafusion_archive_b200/parallel.py), not the
+              product's merge: each rank computes its shard with the ORACLE (test infrastructure), splits
+              its partial aggregate by owner rank, the segments travel over gloo, every rank merges only
+              the keys it owns, the owned segments are gathered, and the result is checked against the
+              oracle on the full data.  Exercises row ranges, the owner function and the merge algebra
+              without a GPU.
   mode nccl : GPUs.  Each rank drives its own B200 through the C ABI with a communicator attached;
-              every rank must end with the global result (dfgpu_aggregate_finish merges over NCCL).
+              every rank must end with the SAME global result (dfgpu_aggregate_finish: owner-partitioned
+              exchange over NCCL), also when one rank saw no rows at all.
 """
 import os
 import sys
@@ -24,6 +28,28 @@ def sort_by_key(cols):
     return [c[o] for c in cols]
 
 
+def aggregate_maybe_empty(ctx, engine, batch, schema, keys, aggs):
+    """ctx.aggregate for a rank that may have no batch: create -> (update) -> finish through the C ABI."""
+    import ctypes as C
+    L = engine.lib()
+    keep = []
+    kptrs, klens, nk = A.make_programs([k.program(schema) for k in keys], keep)
+    aggarr = A.make_aggs([a.lower(schema) for a in aggs], keep)
+    st = C.c_void_p()
+    engine.check(L.dfgpu_aggregate_create(ctx.h, kptrs, klens, nk, aggarr, len(aggs), 0, C.byref(st)))
+    try:
+        if batch is not None:
+            engine.check(L.dfgpu_aggregate_update(st, batch.h))
+        out = C.c_void_p()
+        engine.check(L.dfgpu_aggregate_finish(st, C.byref(out)))
+        r = engine.Result(ctx, out)
+        cols = r.columns()
+        r.free()
+        return cols
+    finally:
+        L.dfgpu_aggregate_free(st)
+
+
 def main():
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -38,9 +64,14 @@ def main():
     if mode == "gloo":
         dist.init_process_group("gloo")
         part = O.aggregate(mine, keys, aggs)
+        segs = parallel.partition_by_owner(part, world)       # what this rank sends to every owner
+        everyone = [None] * world
+        dist.all_gather_object(everyone, segs)                 # (an all-to-all: rank r keeps everyone[s][r])
+        owned = parallel.merge_partials([everyone[s][rank] for s in range(world)], funcs)
+        assert np.all(parallel.owner_of(owned[0], world) == rank)
         gathered = [None] * world
-        dist.all_gather_object(gathered, part)
-        merged = parallel.merge_partials(gathered, funcs)
+        dist.all_gather_object(gathered, owned)
+        merged = sort_by_key([np.concatenate([g[i] for g in gathered]) for i in range(len(owned))])
         fpart = O.filter_project(fmine, fpred, fproj)
         fg = [None] * world
         dist.all_gather_object(fg, fpart)
@@ -85,6 +116,27 @@ def main():
             assert np.array_equal(gm, em), "validity of aggregate %d differs: %r vs %r" % (j, gm, em)
             if em[0]:
                 assert gv[0] == ev[0] or abs(gv[0] - ev[0]) <= 1e-9 * abs(ev[0]), (j, gv, ev)
+        # every rank must hold bit-identical columns (same rows decoded in the same order)
+        import hashlib
+        digest = hashlib.sha256(b"".join(np.ascontiguousarray(c).tobytes() for c in merged)).hexdigest()
+        digs = [None] * world
+        dist.all_gather_object(digs, digest)
+        assert len(set(digs)) == 1, "ranks hold different global results"
+        # one rank contributes no batch at all: it still joins the exchange and gets the global result
+        st_cols = aggregate_maybe_empty(ctx, engine, b if rank == 0 else None, [A.INT64, A.FLOAT64], keys, aggs)
+        exp0 = sort_by_key(O.aggregate(parallel.shard(arrays, 0, world), keys, aggs))
+        got0 = sort_by_key(st_cols)
+        assert np.array_equal(got0[0], exp0[0]) and np.array_equal(got0[1], exp0[1]) and np.array_equal(got0[2], exp0[2])
+        np.testing.assert_allclose(got0[3], exp0[3], rtol=1e-9)
+        assert np.array_equal(got0[4], exp0[4])
+        # fused WHERE under the communicator
+        from datafusion_archive_b200.expr import lit
+        pred = col(1) < lit(0.5)
+        gotp = sort_by_key(ctx.aggregate(b, keys, aggs, pred=pred).columns())
+        keep = arrays[1] < 0.5
+        expp = sort_by_key(O.aggregate([a[keep] for a in arrays], keys, aggs))
+        assert np.array_equal(gotp[0], expp[0]) and np.array_equal(gotp[1], expp[1]) and np.array_equal(gotp[4], expp[4])
+        np.testing.assert_allclose(gotp[3], expp[3], rtol=1e-9)
         fb = ctx.upload(fmine)
         fpart = ctx.filter_project(fb, fpred, fproj).columns()
         fg = [None] * world

@@ -390,7 +390,13 @@ def test_groupby_high_cardinality_layouts(ctx):
 def oracle_filtered_aggregate(arrays, pred, keys, aggs):
     """The reference's wiring for WHERE + GROUP BY: FilterRelation (gathers every column) feeding
     AggregateRelation (context.rs:126-139, 162-192)."""
-    kept = O.filter_project(arrays, pred, [col(i) for i in range(len(arrays))])
+    # (the reference's filter() gathers Float64 / Utf8 only, filter.rs:82-108; integer columns need the
+    # oracle's all-primitives extension, as everywhere in this file)
+    O.set_extensions(filter_all_primitives=True)
+    try:
+        kept = O.filter_project(arrays, pred, [col(i) for i in range(len(arrays))])
+    finally:
+        O.set_extensions(filter_all_primitives=False)
     return O.aggregate(kept, keys, aggs)
 
 

@@ -132,6 +132,45 @@ def test_memory_tables_baseline_queries(ctx):
     assert np.array_equal(k2[o1], e2[0][o2]) and np.array_equal(mx[o1], e2[1][o2])
 
 
+def test_wide_table_where_and_pruned_aggregate(ctx):
+    # 20 numeric columns: (a) WHERE alone gathers every column (filter.rs:55-57) -> several kernel passes over
+    # column groups; (b) SELECT SUM(x) .. WHERE y > 0 uploads two columns and fuses the predicate into the scan
+    n = 50_000
+    rng = np.random.default_rng(9)
+    cols = [rng.random(n) - 0.5 if i % 2 == 0 else rng.integers(-9, 9, n, dtype=np.int64) for i in range(20)]
+    names = ["c%d" % i for i in range(20)]
+    ctx.register_memory("w", list(zip(names, cols)), batch_size=20_000)
+    rel = ctx.sql("SELECT c0, c1, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11, c12, c13, c14, c15, c16, c17, c18, c19 FROM w WHERE c2 > 0.1")
+    got = rel.collect()
+    m = cols[2] > 0.1
+    for i in range(20):
+        assert np.array_equal(np.concatenate([b[i] for b in got]), cols[i][m]), i
+    s, c = ctx.sql("SELECT SUM(c4), COUNT(c4) FROM w WHERE c19 > 0").collect()[0]
+    m = cols[19] > 0
+    assert c[0] == int(m.sum()) and abs(s[0] - cols[4][m].sum()) <= 1e-9 * abs(cols[4][m].sum())
+    k, mx = ctx.sql("SELECT c1, MAX(c18) FROM w WHERE c0 < 0.25 GROUP BY c1").collect()[0]
+    m = cols[0] < 0.25
+    e = O.aggregate([cols[1][m], cols[18][m]], [col(0)], [AggregateFunction("max", col(1))])
+    o1, o2 = np.argsort(k), np.argsort(e[0])
+    assert np.array_equal(k[o1], e[0][o2]) and np.array_equal(mx[o1], e[1][o2])
+
+
+def test_big_aggregate_takes_chunked_upload(ctx):
+    # > 8 Mi rows: GpuAggregateRelation::next streams the batch through dfgpu_aggregate_update_host
+    n = 20_000_000
+    arrays, keys, aggs, k_raw = workloads.c4(n, nkeys=50_000)
+    ctx.register_memory("big4", [("k", arrays[0]), ("v", arrays[1])])
+    k, s, c = ctx.sql("SELECT k, SUM(v), COUNT(v) FROM big4 WHERE v >= 0.5 GROUP BY k").collect()[0]
+    m = arrays[1] >= 0.5
+    cnt = np.bincount(k_raw[m], minlength=50_000)
+    sm = np.bincount(k_raw[m], weights=arrays[1][m], minlength=50_000)
+    present = np.nonzero(cnt)[0]
+    mixed = workloads.mix_keys(present.astype(np.int64))
+    o1, o2 = np.argsort(k), np.argsort(mixed)
+    assert np.array_equal(k[o1], mixed[o2]) and np.array_equal(c[o1], cnt[present][o2].astype(np.uint64))
+    np.testing.assert_allclose(s[o1], sm[present][o2], rtol=1e-9)
+
+
 def test_large_batch_takes_pipelined_path(ctx):
     # >= 4 Mi rows, numeric columns: GpuFilterProjectRelation::next goes through dfgpu_filter_project_host
     n = 5_000_000
