@@ -108,6 +108,30 @@ struct AggParams {
   int has_pred;
   int cond_mm;         // 1: MIN / MAX reductions are skipped when the value read with the probe already covers the row
   int table_hint;      // 1: table loads / reductions carry an L2 evict-last policy
+  // multi-pass scan (tables that outgrow L2): launch `pass_id` of `npass` takes the rows whose hash's top
+  // log2(npass) bits equal pass_id, i.e. whose home slot lies in one contiguous 1/npass of the table
+  int npass, pass_id, pass_shift;
+  // wide keys (k_hash_agg_wide): composite keys of more than 64 bits and keys with Utf8 parts.  Line word 0 is a
+  // TAG (the 64-bit hash of the key tuple, low bit = ready), words 1..kw the key parts: the 64-bit value of a
+  // fixed-width part, or for a Utf8 part a reference (source << 40 | row) to the string of the row that created
+  // the group.  Equal tags are confirmed by comparing every part (strings byte by byte), so hash collisions
+  // just probe on — the reference's Vec<GroupByScalar> equality (aggregate.rs:65-76, 807-852).
+  struct {
+    int kw;
+    int is_utf8[kMaxKeys];
+    const int* off[kMaxKeys];            // this batch's Utf8 key columns
+    const unsigned char* bytes[kMaxKeys];
+    unsigned long long ref_base[kMaxKeys];  // (source index of this batch's column) << UTF8_SRC_SHIFT
+    const Utf8Source* srcs;              // every retained Utf8 key column
+  } wide;
+  // lean kernel (k_hash_agg_lean): one 8-byte key column, one 8-byte argument column, no predicate
+  struct {
+    const unsigned long long* key_col;
+    const unsigned long long* arg_col;
+    unsigned long long* sum_arr;  // additive arrays of SUM / COUNT
+    unsigned long long* cnt_arr;
+    int min_w, max_w;             // words of MIN / MAX in the line
+  } lean;
   PlainSpec plain;
 };
 
@@ -200,6 +224,15 @@ __device__ __forceinline__ void acc_fold_global(int func, int mt, unsigned long 
   }
 }
 
+// Home slot of a key = the TOP log2(cap) bits of its hash.  The top bits of the slot index are then the top
+// bits of the hash whatever the capacity, which is what the multi-pass scan selects rows by (a pass touches
+// one contiguous 1/P of the table, and the assignment of rows to passes survives a table growth).
+__host__ __device__ __forceinline__ int hash_shift(long long cap) {
+  int lg = 0;
+  while ((1ll << lg) < cap) lg++;
+  return 64 - lg;
+}
+__device__ __forceinline__ unsigned long long home_slot(unsigned long long hash, int hshift) { return hshift >= 64 ? 0ull : hash >> hshift; }
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
   x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
@@ -508,7 +541,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
   }
   const int tid = threadIdx.x, lane = tid & 31;
   const long long n = p.row_list ? p.nlist : p.nrows;
-  const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  const int hshift = hash_shift(p.cap);
   // the input is read exactly once: mark its lines evict-first so that they do not displace the table
   const unsigned long long stream_policy = p.stream_hint ? l2_evict_first_policy() : 0ull;
   const unsigned long long tpol = p.table_hint ? l2_evict_last_policy() : 0ull;
@@ -558,7 +591,10 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
     bool probing[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
-      h[r] = mix64(key[r]) & hmask;
+      const unsigned long long hs = mix64(key[r]);
+      h[r] = home_slot(hs, hshift);
+      // multi-pass scan: this launch only takes the rows whose home slot lies in its 1/npass of the table
+      if (p.npass > 1 && (key[r] == EMPTY_KEY ? p.pass_id != 0 : (int)(hs >> p.pass_shift) != p.pass_id)) src.mask &= ~(1u << r);
       probing[r] = ((src.mask >> r) & 1u) && key[r] != EMPTY_KEY && fslot[r] < 0;
       ln[r].w[0] = ln[r].w[1] = ln[r].w[2] = ln[r].w[3] = 0ull;
       if (probing[r]) load_line<true>(p.t, (long long)h[r], ln[r], tpol);
@@ -592,7 +628,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
 #pragma unroll
         for (int r = 0; r < R; r++) {
           if (NULLS && func == DFGPU_AGG_COUNT && !((av >> r) & 1u)) continue;  // COUNT counts non-null values
-          if (FRONT && fslot[r] >= 0) {
+          if (FRONT && fslot[r] >= 0 && ((src.mask >> r) & 1u)) {
             acc_fold_shared(func, mt, &ftab[(1 + a) * FS + fslot[r]], v[r]);
             if ((b >> r) & 1u) bad = true;
           } else if (slot[r] >= 0) {
@@ -619,7 +655,7 @@ __device__ __forceinline__ void hash_agg_body(const AggParams& p, unsigned long 
       const int j = i % FS;
       const unsigned long long key = tb[j];
       if (key == EMPTY_KEY) continue;
-      const unsigned long long h = mix64(key) & hmask;
+      const unsigned long long h = home_slot(mix64(key), hshift);
       Line ln;
       load_line<false>(p.t, (long long)h, ln);
       const long long slot = probe_insert<false>(p.t, p.cap, key, ln, h, false, new_groups);
@@ -641,6 +677,260 @@ template <int NC, bool PF, bool FRONT>
 __global__ void __launch_bounds__(AG_THREADS, 4) k_hash_agg_plain(const __grid_constant__ AggParams p) {
   extern __shared__ unsigned long long s_front[];
   hash_agg_body<PlainSrc<NC, PF>, FRONT, false>(p, s_front);
+}
+
+// K5, lean form: the canonical GROUP BY shape — one 8-byte integer key column, one 8-byte argument column, any
+// subset M of {MIN = 1, MAX = 2, SUM = 4, COUNT = 8} over it, no WHERE — with everything that is dynamic in the
+// generic body (loops over keys / arguments / aggregates, dtype and function switches, layout arithmetic)
+// resolved at compile time: ~60 instructions per row instead of ~300 (ncu: the generic kernels are issue-bound
+// well before the LSU / L2 ceiling of their scattered operations).  Same table, same protocol.
+template <int M, int MT>
+__global__ void __launch_bounds__(AG_THREADS, 5) k_hash_agg_lean(const __grid_constant__ AggParams p) {
+  constexpr bool HAS_MIN = (M & 1) != 0, HAS_MAX = (M & 2) != 0, HAS_SUM = (M & 4) != 0, HAS_CNT = (M & 8) != 0;
+  constexpr int LW = (HAS_MIN && HAS_MAX) ? 4 : ((HAS_MIN || HAS_MAX) ? 2 : 1);  // the hybrid layout's line for this M (host-checked)
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long n = p.nrows;
+  const unsigned long long* __restrict__ kc = p.lean.key_col + p.row_begin;
+  const unsigned long long* __restrict__ vc = p.lean.arg_col + p.row_begin;
+  unsigned long long* const base = p.t.base;
+  const int hshift = hash_shift(p.cap);
+  const unsigned long long smask = (unsigned long long)p.cap - 1ull;
+  const unsigned long long policy = p.stream_hint ? l2_evict_first_policy() : 0ull;
+  constexpr int TILE = AG_THREADS * 2;
+  for (long long tb = (long long)blockIdx.x * TILE; tb < n; tb += (long long)gridDim.x * TILE) {
+    unsigned long long filled = 0;
+    if (lane == 0) filled = __ldcg(&p.counters[0]);
+    filled = __shfl_sync(0xffffffffu, filled, 0);
+    const bool full = (long long)filled >= p.max_groups;
+    const long long i = tb + 2ll * tid;
+    const bool any = i < n, both = i + 1 < n;
+    unsigned long long k[2] = {0ull, 0ull}, v[2] = {0ull, 0ull};
+    if (any) {
+      ld_pair64(kc, i, both, policy, k);
+      ld_pair64(vc, i, both, policy, v);
+    }
+    unsigned long long slot[2];
+    Line ln[2];
+    bool act[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const unsigned long long hs = mix64(k[r]);
+      slot[r] = home_slot(hs, hshift);
+      act[r] = (r == 0 ? any : both) && (p.npass == 1 || (k[r] == EMPTY_KEY ? p.pass_id == 0 : (int)(hs >> p.pass_shift) == p.pass_id));
+      if (act[r] && k[r] != EMPTY_KEY) {
+        const unsigned long long* q = base + slot[r] * LW;
+        if (LW == 4) asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ln[r].w[0]), "=l"(ln[r].w[1]), "=l"(ln[r].w[2]), "=l"(ln[r].w[3]) : "l"(q) : "memory");
+        else if (LW == 2) asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(ln[r].w[0]), "=l"(ln[r].w[1]) : "l"(q) : "memory");
+        else asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(ln[r].w[0]) : "l"(q) : "memory");
+      }
+    }
+    unsigned new_groups = 0;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      if (!act[r]) continue;
+      bool have_line = true;
+      if (k[r] == EMPTY_KEY) {  // the one key value that collides with the empty marker
+        if (__ldcg(&p.counters[2]) == 0ull) p.counters[2] = 1ull;
+        slot[r] = (unsigned long long)p.cap;
+        have_line = false;
+      } else {
+        bool found = false;
+        for (int probes = 0; probes < AG_MAX_PROBE; ++probes) {
+          if (ln[r].w[0] == k[r]) { found = true; break; }
+          if (ln[r].w[0] == EMPTY_KEY) {
+            if (full) break;
+            const unsigned long long old = atomicCAS(base + slot[r] * LW, EMPTY_KEY, k[r]);
+            if (old == EMPTY_KEY) { new_groups++; found = true; break; }
+            if (old == k[r]) { found = true; break; }
+          }
+          slot[r] = (slot[r] + 1ull) & smask;
+          const unsigned long long* q = base + slot[r] * LW;
+          if (LW == 4) asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(ln[r].w[0]), "=l"(ln[r].w[1]), "=l"(ln[r].w[2]), "=l"(ln[r].w[3]) : "l"(q) : "memory");
+          else if (LW == 2) asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(ln[r].w[0]), "=l"(ln[r].w[1]) : "l"(q) : "memory");
+          else asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(ln[r].w[0]) : "l"(q) : "memory");
+        }
+        if (!found) {  // table refuses new keys: the row is replayed after the table has grown
+          const unsigned long long at = atomicAdd(&p.counters[1], 1ull);
+          p.ovf_rows[at] = (unsigned)(p.row_begin + i + r);
+          continue;
+        }
+      }
+      unsigned long long* const line = base + slot[r] * LW;
+      if (HAS_MIN || HAS_MAX) {
+        if (!is_nan_val(v[r], MT)) {  // f64::min / f64::max ignore NaN (aggregate.rs:139-140, 208-209)
+          const unsigned long long e = ord_enc(v[r], MT);
+          if (HAS_MIN && (!have_line || !p.cond_mm || e < line_word(ln[r], p.lean.min_w))) atomicMin(line + p.lean.min_w, e);
+          if (HAS_MAX && (!have_line || !p.cond_mm || e > line_word(ln[r], p.lean.max_w))) atomicMax(line + p.lean.max_w, e);
+        }
+      }
+      if (HAS_SUM) {
+        if (MT == MT_F64) atomicAdd((double*)(p.lean.sum_arr + slot[r]), u2d(v[r]));
+        else atomicAdd(p.lean.sum_arr + slot[r], v[r]);
+      }
+      if (HAS_CNT) atomicAdd(p.lean.cnt_arr + slot[r], 1ull);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+    if (lane == 0 && new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+  }
+}
+
+// ---- wide / mixed keys ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long wide_tag(unsigned long long h) {  // ready form: low bit set, never EMPTY_KEY
+  unsigned long long t = h | 1ull;
+  if (t == EMPTY_KEY) t ^= 2ull;
+  return t;
+}
+__device__ __forceinline__ bool utf8_equal(const int* off_a, const unsigned char* bytes_a, long long ra, const Utf8Source& sb, long long rb) {
+  const int sa = off_a[ra], la = off_a[ra + 1] - sa, s2 = sb.off[rb], lb = sb.off[rb + 1] - s2;
+  if (la != lb) return false;
+  for (int i = 0; i < la; i++)
+    if (bytes_a[sa + i] != sb.bytes[s2 + i]) return false;
+  return true;
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* q) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(q) : "memory");
+  return v;
+}
+
+// K5 for wide keys.  Claim protocol of a slot: CAS the tag word EMPTY -> tag & ~1 (busy), store the key parts,
+// fence, store tag | 1 (ready).  A row that meets a busy slot with its own tag polls briefly and otherwise
+// defers itself to the replay list (counters[5] counts those: they need no table growth, the slot is
+// ready by the time the replay runs), so no thread ever waits on another one indefinitely.
+template <int DEPTH, bool NULLS>
+__global__ void __launch_bounds__(AG_THREADS) k_hash_agg_wide(const __grid_constant__ AggParams p) {
+  typedef InterpSrc<DEPTH, NULLS> Src;
+  constexpr int R = Src::R;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const long long n = p.row_list ? p.nlist : p.nrows;
+  const int hshift = hash_shift(p.cap);
+  const unsigned long long smask = (unsigned long long)p.cap - 1ull;
+  const int KW = p.wide.kw;
+  bool bad = false;
+  constexpr int TILE = AG_THREADS * R;
+  for (long long tb = (long long)blockIdx.x * TILE; tb < n; tb += (long long)gridDim.x * TILE) {
+    unsigned long long filled = 0;
+    if (lane == 0) filled = __ldcg(&p.counters[0]);
+    filled = __shfl_sync(0xffffffffu, filled, 0);
+    const bool full = (long long)filled >= p.max_groups;
+    Src src;
+    src.load(p, tb, n, tid, 0ull);
+    src.prepare(p);
+    // key parts: value of a fixed-width part; for a Utf8 part the program reads the string's 64-bit hash
+    unsigned long long part[kMaxKeys][R];
+    unsigned long long hsh[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) hsh[r] = 0x9e3779b97f4a7c15ull;
+    for (int k = 0; k < kMaxKeys; k++) {
+      if (k >= KW) break;
+      unsigned long long v[R];
+      src.key(p, k, v);
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        part[k][r] = v[r];
+        hsh[r] = mix64(hsh[r] ^ (v[r] + 0x9e3779b97f4a7c15ull * (unsigned long long)(k + 1)));
+      }
+    }
+    long long slot[R];
+    unsigned new_groups = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      slot[r] = -1;
+      if (!((src.mask >> r) & 1u)) continue;
+      const long long row = src.g.rows[r];
+      const unsigned long long ready = wide_tag(hsh[r]), busy = ready & ~1ull;
+      unsigned long long h = home_slot(hsh[r], hshift);
+      bool deferred = false;
+      for (int probes = 0; probes < AG_MAX_PROBE; ++probes) {
+        unsigned long long* line = p.t.key((long long)h);
+        unsigned long long t = ld_volatile_u64(line);
+        if (t == EMPTY_KEY) {
+          if (full) break;
+          t = atomicCAS(line, EMPTY_KEY, busy);
+          if (t == EMPTY_KEY) {  // claimed: publish the key parts, then the ready tag
+            for (int k = 0; k < KW; k++) line[1 + k] = p.wide.is_utf8[k] ? (p.wide.ref_base[k] | (unsigned long long)row) : part[k][r];
+            __threadfence();
+            atomicExch(line, ready);
+            new_groups++;
+            slot[r] = (long long)h;
+            break;
+          }
+        }
+        if ((t | 1ull) == ready) {
+          for (int spin = 0; t == busy && spin < 64; spin++) { __nanosleep(64); t = ld_volatile_u64(line); }
+          if (t == busy) { deferred = true; break; }
+          __threadfence();
+          bool same = true;
+          for (int k = 0; same && k < KW; k++) {
+            const unsigned long long w = __ldcg(line + 1 + k);
+            if (p.wide.is_utf8[k]) {
+              const Utf8Source& sc = p.wide.srcs[w >> UTF8_SRC_SHIFT];
+              same = utf8_equal(p.wide.off[k], p.wide.bytes[k], row, sc, (long long)(w & ((1ull << UTF8_SRC_SHIFT) - 1ull)));
+            } else {
+              same = w == part[k][r];
+            }
+          }
+          if (same) { slot[r] = (long long)h; break; }
+        }
+        h = (h + 1ull) & smask;
+      }
+      if (slot[r] < 0) {
+        const unsigned long long at = atomicAdd(&p.counters[1], 1ull);
+        p.ovf_rows[at] = (unsigned)row;
+        if (deferred) atomicAdd(&p.counters[5], 1ull);
+      }
+    }
+    for (int g = 0; g < p.nargs; g++) {
+      unsigned long long v[R];
+      unsigned av;
+      const unsigned b = src.arg(p, g, v, av);
+      for (int a = 0; a < p.naggs; a++) {
+        if (p.agg_arg[a] != g) continue;
+        const int func = p.aggs[a].func, mt = p.aggs[a].mtype;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (NULLS && func == DFGPU_AGG_COUNT && !((av >> r) & 1u)) continue;
+          if (slot[r] >= 0) {
+            acc_fold_global(func, mt, p.t.val(slot[r], a), v[r]);
+            if ((b >> r) & 1u) bad = true;
+          }
+        }
+      }
+    }
+    bad = bad || src.bad != 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) new_groups += __shfl_xor_sync(0xffffffffu, new_groups, o);
+    if (lane == 0 && new_groups) atomicAdd(&p.counters[0], (unsigned long long)new_groups);
+  }
+  if (bad) p.counters[3] = 1ull;
+}
+
+// Re-insertion of the (distinct) groups of a wide-key table into a bigger one: every entry goes to the first
+// empty slot after its home; no key comparison is needed because the source table holds each key once.
+struct WideMoveParams {
+  TableLayout from, to;
+  long long from_cap, to_cap;
+  int kw, naggs;
+};
+__global__ void __launch_bounds__(256) k_wide_move(const __grid_constant__ WideMoveParams p) {
+  const int hshift = hash_shift(p.to_cap);
+  const unsigned long long smask = (unsigned long long)p.to_cap - 1ull;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < p.from_cap; s += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long* src = p.from.key(s);
+    const unsigned long long tag = src[0];
+    if (tag == EMPTY_KEY) continue;
+    unsigned long long h = home_slot(tag & ~1ull, hshift);  // the tag IS the hash (but for its low bit): same home rule as the scan
+    for (;;) {
+      unsigned long long* dst = p.to.key((long long)h);
+      if (atomicCAS(dst, EMPTY_KEY, tag) == EMPTY_KEY) {
+        for (int k = 0; k < p.kw; k++) dst[1 + k] = src[1 + k];
+        for (int a = 0; a < p.naggs; a++) *p.to.val((long long)h, a) = *p.from.val(s, a);
+        break;
+      }
+      h = (h + 1ull) & smask;
+    }
+  }
 }
 
 // K4: no GROUP BY.  Per-thread accumulators live in shared memory (one 8-byte cell per thread per
@@ -814,6 +1104,8 @@ struct CompactParams {
   int sentinel_used;
   int nkeys, naggs, raw;
   long long raw_stride;  // raw output: element idx of every raw array lives at idx * raw_stride (0 = 1: dense arrays)
+  int wide_kw;           // wide keys: line words 1..wide_kw are the key parts (a Utf8 part = a string reference)
+  int key_is_utf8[kMaxKeys];
   AggDesc aggs[kMaxAggs];
   // aggregates over the same argument expression (MIN(v), MAX(v), SUM(v)) share one evaluation:
   // programs [nkeys, nkeys + nargs) are the DISTINCT argument programs, agg_arg[a] picks one
@@ -851,6 +1143,12 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
       for (int a = 0; a < p.naggs; a++) ((unsigned long long*)p.out_vals[a])[at] = *p.t.val(s, a);
     } else {
       for (int k = 0; k < p.nkeys; k++) {
+        if (p.wide_kw) {
+          const unsigned long long w = p.t.key(s)[1 + k];
+          if (p.key_is_utf8[k]) ((unsigned long long*)p.out_keys[k])[idx] = w;  // string reference, gathered by the host
+          else store_elem(p.out_keys[k], p.key_dtype[k], idx, w);
+          continue;
+        }
         unsigned long long v = (key >> p.key_shift[k]) & p.key_mask[k];
         store_elem(p.out_keys[k], p.key_dtype[k], idx, v);
       }
@@ -879,7 +1177,7 @@ struct MergeParams {
 };
 
 __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergeParams p) {
-  const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  const int hshift = hash_shift(p.cap);
   unsigned new_groups = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     const long long at = p.in_stride ? i * p.in_stride : i;
@@ -889,7 +1187,7 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
       p.counters[2] = 1ull;
       slot = p.cap;
     } else {
-      const unsigned long long h = mix64(key) & hmask;
+      const unsigned long long h = home_slot(mix64(key), hshift);
       Line ln;
       load_line<false>(p.t, (long long)h, ln);
       slot = probe_insert<false>(p.t, p.cap, key, ln, h, false, new_groups);
@@ -906,7 +1204,7 @@ __global__ void __launch_bounds__(256) k_merge(const __grid_constant__ MergePara
 // keys: owner = bits of mix64(key) that the table slot does not use.
 constexpr int AG_MAX_WORLD = 64;
 __device__ __forceinline__ int owner_of(unsigned long long key, int world) {
-  return key == EMPTY_KEY ? 0 : (int)((mix64(key) >> 44) % (unsigned long long)world);
+  return key == EMPTY_KEY ? 0 : (int)((mix64(key) & 0xffffffffull) % (unsigned long long)world);
 }
 struct OwnerParams {
   const unsigned long long* keys;              // raw (packed) keys of the local groups
@@ -983,11 +1281,12 @@ struct VerifyParams {
 };
 __global__ void __launch_bounds__(256) k_utf8_group_verify(const __grid_constant__ VerifyParams p) {
   const unsigned long long hmask = (unsigned long long)p.cap - 1ull;
+  const int hshift = hash_shift(p.cap);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     const unsigned long long key = p.hashes[i];
     long long slot = p.cap;
     if (key != EMPTY_KEY) {
-      unsigned long long h = mix64(key) & hmask;
+      unsigned long long h = home_slot(mix64(key), hshift);
       for (;;) {
         const unsigned long long cur = __ldcg(p.t.key((long long)h));
         if (cur == key) { slot = (long long)h; break; }
@@ -1046,6 +1345,10 @@ struct dfgpu_aggstate {
   bool aos = false;        // "line" layout: every accumulator shares the line with the key (tables beyond L2)
   std::vector<dfgpu_insn> pred_prog;  // fused WHERE predicate (dfgpu_aggregate_set_predicate); empty = none
   bool use_front = false;  // route rows through the per-CTA shared-memory front table
+  int npass = 1;           // scan passes per big batch (tables that outgrow L2, see AggParams)
+  // wide keys: composite keys of more than 64 bits or with Utf8 parts (k_hash_agg_wide)
+  bool wide = false;
+  std::vector<int> key_is_utf8;
   // Utf8 GROUP BY key (aggregate.rs:842-847): grouped by a 64-bit string hash; the last accumulator is a
   // hidden MIN(source << 40 | row) = representative row of the group; the key columns of all batches are
   // retained so the representatives' strings can be gathered at finish
@@ -1130,12 +1433,12 @@ bool hybrid_enabled() {
   static const bool off = getenv("DFGPU_AGG_HYBRID") && atoi(getenv("DFGPU_AGG_HYBRID")) == 0;  // A/B switch: 0 = plain SoA (round-1 layout)
   return !off;
 }
-void layout_shape(const std::vector<AggDesc>& descs, int naggs, int nkeys, bool line_mode, long long* lw, int* n_add, signed char* loc) {
+void layout_shape(const std::vector<AggDesc>& descs, int naggs, int nkeys, bool line_mode, long long* lw, int* n_add, signed char* loc, int kw = 0) {
   *lw = 1;
   *n_add = 0;
-  if (nkeys > 0 && line_mode) {
-    while (*lw < 1 + naggs) *lw <<= 1;
-    for (int a = 0; a < naggs; a++) loc[a] = (signed char)(1 + a);
+  if (nkeys > 0 && (line_mode || kw > 0)) {  // wide keys: tag, kw key parts, then every accumulator, all in the line
+    while (*lw < 1 + kw + naggs) *lw <<= 1;
+    for (int a = 0; a < naggs; a++) loc[a] = (signed char)(1 + kw + a);
     return;
   }
   int nmm = 0;
@@ -1145,6 +1448,10 @@ void layout_shape(const std::vector<AggDesc>& descs, int naggs, int nkeys, bool 
     else loc[a] = (signed char)~((*n_add)++);
   }
   while (*lw < 1 + nmm) *lw <<= 1;
+}
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 bool want_aos(long long groups, const std::vector<AggDesc>& descs, int naggs) {
   static const char* force = getenv("DFGPU_AGG_LAYOUT");  // A/B switch: "line" | "hybrid"
@@ -1157,14 +1464,15 @@ bool want_aos(long long groups, const std::vector<AggDesc>& descs, int naggs) {
   const long long cap = std::max(AG_MIN_CAP, next_pow2(2 * groups));
   const long long line_hot = std::min(cap * 8 * lw, groups * std::max<long long>(32, 8 * lw));
   const long long arr_hot = std::min(cap * 8, groups * 32);
-  return line_hot + n_add * arr_hot > AG_SOA_L2_BUDGET;
+  static const long long budget = std::max<long long>(AG_SOA_L2_BUDGET, (long long)env_int("DFGPU_AGG_PASS_MB", 32) * env_int("DFGPU_AGG_MAX_PASSES", 4) << 20);
+  return line_hot + n_add * arr_hot > budget;
 }
 
-TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, int nkeys, const std::vector<AggDesc>& descs, long long cap, bool aos) {
+TableLayout table_alloc(dfgpu_ctx* ctx, int naggs, int nkeys, const std::vector<AggDesc>& descs, long long cap, bool aos, int kw = 0) {
   InitParams ip;
   memset(&ip, 0, sizeof(ip));
   int n_add = 0;
-  layout_shape(descs, naggs, nkeys, aos, &ip.t.lw, &n_add, ip.t.loc);
+  layout_shape(descs, naggs, nkeys, aos, &ip.t.lw, &n_add, ip.t.loc, kw);
   const size_t line_words = size_t(cap + 1) * size_t(ip.t.lw);
   const size_t words = line_words + size_t(n_add) * size_t(cap + 1);
   ip.t.base = (unsigned long long*)ctx->alloc(words * 8);  // >= 256-byte aligned: lines of up to 32 bytes never straddle a sector
@@ -1248,6 +1556,27 @@ void table_grow(dfgpu_aggstate* st, long long new_cap) {
   st->cap = new_cap;
 }
 
+// Hot bytes of the hybrid layout for `groups` groups (see want_aos) and the number of scan passes that
+// keeps the part of the table one pass touches L2 resident.
+long long hybrid_hot_bytes(long long groups, const std::vector<AggDesc>& descs, int naggs) {
+  long long lw;
+  int n_add;
+  signed char loc[kMaxAggs];
+  layout_shape(descs, naggs, 1, false, &lw, &n_add, loc);
+  const long long cap = std::max(AG_MIN_CAP, next_pow2(2 * groups));
+  return std::min(cap * 8 * lw, groups * std::max<long long>(32, 8 * lw)) + n_add * std::min(cap * 8, groups * 32);
+}
+int passes_for(long long groups, const std::vector<AggDesc>& descs, int naggs) {
+  static const int forced = env_int("DFGPU_AGG_PASSES", 0);          // A/B switch: 1 | 2 | 4 | 8
+  static const int pass_mb = env_int("DFGPU_AGG_PASS_MB", 32);       // hot megabytes one pass may touch
+  static const int max_passes = env_int("DFGPU_AGG_MAX_PASSES", 4);
+  if (forced > 0) return forced;
+  const long long hot = hybrid_hot_bytes(groups, descs, naggs);
+  int np = 1;
+  while (np < max_passes && hot / np > ((long long)pass_mb << 20)) np <<= 1;
+  return hot / np > ((long long)pass_mb << 20) ? 1 : np;  // beyond max_passes x pass_mb: one pass over the line layout
+}
+
 // Launch one scan kernel.  FRONT launches admit the keys of every CTA's front table unconditionally when
 // the CTA retires, so the fill limit of the global path is lowered by what they can add (grid x front
 // slots): the table stays at most half full and the front merge always finds a slot.
@@ -1271,6 +1600,21 @@ template <int DEPTH>
 void launch_hash_agg(dfgpu_ctx* ctx, AggParams& p, long long n, bool front) {
   if (front) launch_scan(ctx, k_hash_agg<DEPTH, true, false>, p, n, true);
   else launch_scan(ctx, k_hash_agg<DEPTH, false, false>, p, n, false);
+}
+template <int M>
+void launch_lean_m(dfgpu_ctx* ctx, AggParams& p, long long n, int mt) {
+  if (mt == MT_F64) launch_scan(ctx, k_hash_agg_lean<M, MT_F64>, p, n, false);
+  else if (mt == MT_I) launch_scan(ctx, k_hash_agg_lean<M, MT_I>, p, n, false);
+  else launch_scan(ctx, k_hash_agg_lean<M, MT_U>, p, n, false);
+}
+void launch_lean(dfgpu_ctx* ctx, AggParams& p, long long n, int mask, int mt) {
+  switch (mask) {
+#define DF_LEAN(M) case M: launch_lean_m<M>(ctx, p, n, mt); break;
+    DF_LEAN(1) DF_LEAN(2) DF_LEAN(3) DF_LEAN(4) DF_LEAN(5) DF_LEAN(6) DF_LEAN(7) DF_LEAN(8)
+    DF_LEAN(9) DF_LEAN(10) DF_LEAN(11) DF_LEAN(12) DF_LEAN(13) DF_LEAN(14) DF_LEAN(15)
+#undef DF_LEAN
+    default: fail(DFGPU_ERR_INTERNAL, "lean kernel: bad aggregate mask");
+  }
 }
 template <int DEPTH, bool NULLS = false>
 void launch_reduce(dfgpu_ctx* ctx, const AggParams& p, long long n) {
@@ -1435,6 +1779,9 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
       ukey = &batch->cols[size_t(st->key_progs[0][0].col)];
     unsigned long long* d_hash = nullptr;
     struct HashFree { dfgpu_ctx* c; unsigned long long** p; ~HashFree() { c->free(*p); } } hash_free{ctx, &d_hash};
+    std::vector<const DevColumn*> wide_ucols;    // per key part: its Utf8 column in this batch (or null)
+    std::vector<unsigned long long*> wide_hashes;  // string hashes of the Utf8 parts
+    struct HashesFree { dfgpu_ctx* c; std::vector<unsigned long long*>* v; ~HashesFree() { for (auto* q : *v) c->free(q); } } hashes_free{ctx, &wide_hashes};
     if (ukey) {
       if (st->typed && !st->utf8_key) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
       if (!st->typed && st->naggs >= kMaxAggs) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY key with " + std::to_string(kMaxAggs) + " aggregates");
@@ -1445,10 +1792,25 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
       pb.add_synthetic_column(d_hash, DFGPU_UINT64);
       kdt.push_back(DFGPU_UINT64);
     } else {
+      // key parts: integer expressions, and plain Utf8 columns (hashed here; the scan reads the hash as a column)
       for (int k = 0; k < st->nkeys; k++) {
-        int pi = pb.add(st->key_progs[size_t(k)].data(), int(st->key_progs[size_t(k)].size()), "GROUP BY expression");
+        const auto& kp = st->key_progs[size_t(k)];
+        const DevColumn* uc = nullptr;
+        if (kp.size() == 1 && kp[0].op == DFGPU_OP_COL && kp[0].col >= 0 && size_t(kp[0].col) < batch->cols.size() &&
+            batch->cols[size_t(kp[0].col)].dtype == DFGPU_UTF8)
+          uc = &batch->cols[size_t(kp[0].col)];
+        wide_ucols.push_back(uc);
+        if (uc) {
+          unsigned long long* dh = (unsigned long long*)ctx->alloc(size_t(batch->nrows > 0 ? batch->nrows : 1) * 8);
+          wide_hashes.push_back(dh);
+          utf8_hash(ctx, *uc, batch->nrows, dh);
+          pb.add_synthetic_column(dh, DFGPU_UINT64);
+          kdt.push_back(DFGPU_UTF8);
+          continue;
+        }
+        int pi = pb.add(kp.data(), int(kp.size()), "GROUP BY expression");
         int dt = pb.out_dtype(pi);
-        if (dt == DFGPU_UTF8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys are supported as a single plain column only");
+        if (dt == DFGPU_UTF8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys must be plain columns");
         if (!is_int(dt)) fail(DFGPU_ERR_EXECUTION, "Unsupported GROUP BY data type");  // aggregate.rs:848-850
         kdt.push_back(dt);
       }
@@ -1518,18 +1880,29 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
       st->key_dtypes = kdt;
       st->descs = descs;
       int bits = 0;
+      bool any_utf8 = false;
       for (int k = st->nkeys - 1; k >= 0; k--) {  // last key in the low bits
-        int w = dtype_width(kdt[size_t(k)]) * 8;
-        st->key_shift.insert(st->key_shift.begin(), bits);
+        const bool u = !ukey && kdt[size_t(k)] == DFGPU_UTF8;
+        any_utf8 = any_utf8 || u;
+        int w = u ? 64 : dtype_width(kdt[size_t(k)]) * 8;
+        st->key_shift.insert(st->key_shift.begin(), bits > 63 ? 0 : bits);
         st->key_mask.insert(st->key_mask.begin(), w == 64 ? ~0ull : ((1ull << w) - 1ull));
+        st->key_is_utf8.insert(st->key_is_utf8.begin(), u ? 1 : 0);
         bits += w;
       }
-      if (bits > 64) fail(DFGPU_ERR_NOT_IMPLEMENTED, "composite GROUP BY keys wider than 64 bits");
+      // more than 64 key bits, or Utf8 parts next to other parts: tagged slots with full key comparison
+      st->wide = !ukey && (bits > 64 || any_utf8);
       if (st->nkeys == 1) st->key_mask[0] = ~0ull;  // single key: keep the sign-extended 64-bit value
       st->typed = true;
       st->cap = st->nkeys == 0 ? 0 : std::max(AG_MIN_CAP, next_pow2(2 * st->expected));
+      if (st->wide) {
+        st->aos = true;
+        st->t = table_alloc(ctx, st->naggs, st->nkeys, st->descs, st->cap, true, st->nkeys);
+      } else {
       st->aos = st->nkeys > 0 && want_aos(st->expected, st->descs, st->naggs);
+      st->npass = (st->nkeys > 0 && !st->aos && st->expected > 0) ? passes_for(st->expected, st->descs, st->naggs) : 1;
       st->t = table_alloc(ctx, st->naggs, st->nkeys, st->descs, st->cap, st->aos);
+      }
     } else {
       if (kdt != st->key_dtypes) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
       for (int a = 0; a < st->naggs; a++)
@@ -1610,6 +1983,95 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
       return;
     }
 
+    if (st->wide) {
+      if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "composite GROUP BY keys wider than 64 bits or with Utf8 parts under a multi-GPU communicator");
+      // retain this batch's Utf8 key columns: a group's string lives in the batch whose row created it
+      p.wide.kw = st->nkeys;
+      bool new_src = false;
+      for (int k = 0; k < st->nkeys; k++) {
+        p.wide.is_utf8[k] = st->key_is_utf8[size_t(k)];
+        const DevColumn* uc = wide_ucols[size_t(k)];
+        if (!uc) continue;
+        if (st->utf8_srcs.size() >= (1u << 20)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than 2^20 retained Utf8 GROUP BY key columns");
+        const size_t ob = size_t(batch->nrows + 1) * 4, vb = uc->values_bytes ? uc->values_bytes : 1;
+        int* off = (int*)ctx->alloc(ob);
+        unsigned char* bytes = (unsigned char*)ctx->alloc(vb);
+        DF_CUDA(cudaMemcpyAsync(off, uc->offsets, ob, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (uc->values_bytes) DF_CUDA(cudaMemcpyAsync(bytes, uc->values, uc->values_bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        p.wide.off[k] = off;
+        p.wide.bytes[k] = bytes;
+        p.wide.ref_base[k] = (unsigned long long)st->utf8_srcs.size() << UTF8_SRC_SHIFT;
+        st->utf8_owned.push_back(off);
+        st->utf8_owned.push_back(bytes);
+        st->utf8_srcs.push_back(Utf8Source{off, bytes});
+        new_src = true;
+      }
+      if (new_src) {
+        ctx->free(st->d_utf8_srcs);
+        st->d_utf8_srcs = (Utf8Source*)ctx->alloc(st->utf8_srcs.size() * sizeof(Utf8Source));
+        DF_CUDA(cudaMemcpyAsync(st->d_utf8_srcs, st->utf8_srcs.data(), st->utf8_srcs.size() * sizeof(Utf8Source), cudaMemcpyHostToDevice, ctx->stream));
+        DF_CUDA(cudaStreamSynchronize(ctx->stream));  // utf8_srcs may reallocate on the next batch
+      }
+      p.wide.srcs = st->d_utf8_srcs;
+      unsigned* wovf[2] = {(unsigned*)ctx->alloc(size_t(batch->nrows) * 4), nullptr};
+      struct WFreer { dfgpu_ctx* c; unsigned** o; ~WFreer() { c->free(o[0]); c->free(o[1]); } } wfreer{ctx, wovf};
+      auto wide_grow = [&](long long new_cap) {
+        TableLayout nt = table_alloc(ctx, st->naggs, st->nkeys, st->descs, new_cap, true, st->nkeys);
+        WideMoveParams mp;
+        memset(&mp, 0, sizeof(mp));
+        mp.from = st->t;
+        mp.to = nt;
+        mp.from_cap = st->cap;
+        mp.to_cap = new_cap;
+        mp.kw = st->nkeys;
+        mp.naggs = st->naggs;
+        k_wide_move<<<grid_for(ctx, st->cap, 256, 8), 256, 0, ctx->stream>>>(mp);
+        DF_CUDA(cudaGetLastError());
+        ctx->launches++;
+        DF_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->free(st->t.base);
+        st->t = nt;
+        st->cap = new_cap;
+      };
+      int cur = 0;
+      const unsigned* list = nullptr;
+      long long nlist = 0;
+      for (int round = 0;; round++) {
+        if (round > 60) fail(DFGPU_ERR_INTERNAL, "hash table growth did not converge");
+        p.t = st->t;
+        p.cap = st->cap;
+        p.max_groups = st->cap / 2;
+        p.row_begin = 0;
+        p.nrows = batch->nrows;
+        p.row_list = list;
+        p.nlist = nlist;
+        p.ovf_rows = wovf[cur];
+        p.npass = 1;
+        DF_CUDA(cudaMemsetAsync(st->d_counters + 1, 0, 8, ctx->stream));
+        DF_CUDA(cudaMemsetAsync(st->d_counters + 5, 0, 8, ctx->stream));
+        const long long n = list ? nlist : p.nrows;
+        if (p.ps.has_nulls) launch_scan(ctx, k_hash_agg_wide<8, true>, p, n, false);
+        else launch_scan(ctx, k_hash_agg_wide<8, false>, p, n, false);
+        unsigned long long c[8];
+        read_counters(st, c);
+        if (c[3]) fail(DFGPU_ERR_ARROW, "DivideByZero");
+        st->ngroups = (long long)c[0];
+        const long long novf = (long long)c[1], deferred = (long long)c[5];
+        tr.mark("scan kernel (wide keys)");
+        if (novf == 0) {
+          if (st->ngroups > st->cap / 2) wide_grow(st->cap * 4);
+          break;
+        }
+        // rows that only met a slot still being published need no bigger table: replay them as they are
+        if (!(novf == deferred && st->ngroups <= st->cap / 2)) wide_grow(st->cap * 4);
+        list = wovf[cur];
+        nlist = novf;
+        cur ^= 1;
+        if (!wovf[cur]) wovf[cur] = (unsigned*)ctx->alloc(size_t(batch->nrows) * 4);
+      }
+      return;
+    }
+
     // Plain-column fast path: keys and arguments are plain 4/8-byte columns, the WHERE clause (if any) a
     // chain of column comparisons -> the interpreter-free kernel with 128-bit loads.
     bool use_plain = false;
@@ -1668,6 +2130,21 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
       if (ok) p.plain = sp;
       use_plain = ok;
     }
+    // lean kernel: one 8-byte integer key column, one 8-byte argument column, distinct MIN/MAX/SUM/COUNT, no WHERE
+    int lean_mask = 0, lean_mt = 0;
+    {
+      static const bool off = getenv("DFGPU_AGG_LEAN") && atoi(getenv("DFGPU_AGG_LEAN")) == 0;  // A/B switch
+      auto w8 = [](int dt) { return dt == DFGPU_FLOAT64 || dt == DFGPU_INT64 || dt == DFGPU_UINT64; };
+      bool ok = !off && use_plain && !has_pred && st->nkeys == 1 && nargs == 1 && w8(p.ps.cols[p.plain.key_slot[0]].dtype) &&
+                w8(p.ps.cols[p.plain.arg_slot[0]].dtype);
+      for (int a = 0; ok && a < st->naggs; a++) {
+        const int bit = 1 << (st->descs[size_t(a)].func - 1);  // MIN 1, MAX 2, SUM 4, COUNT 8
+        ok = !(lean_mask & bit);
+        lean_mask |= bit;
+      }
+      if (ok) lean_mt = mtype_of(p.ps.cols[p.plain.arg_slot[0]].dtype);
+      else lean_mask = 0;
+    }
 
     // GROUP BY: run, then replay rows that could not get a slot after growing the table.
     // First big batch with no cardinality hint: a 1 Mi-row prefix is aggregated first; the number of
@@ -1716,24 +2193,54 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
         }
         // (A persisting-L2 access-policy window over the table was measured in round 2 and removed: the scan
         // went from 1.57 to 7.8 ms at 1e5 groups and from 3.4 to 15 ms at 1e6, profiles/r02a_l2persist.txt.)
-        if (p.ps.has_nulls) launch_scan(ctx, k_hash_agg<8, false, true>, p, n, false);
-        else if (use_plain && !list && (p.row_begin & 1) == 0) {
-          static const bool no_pf = getenv("DFGPU_AGG_PREFETCH") && atoi(getenv("DFGPU_AGG_PREFETCH")) == 0;  // A/B switch
-          const bool two = p.plain.ncols <= 2;
-          if (front) {
-            if (two) launch_scan(ctx, k_hash_agg_plain<2, false, true>, p, n, true);
-            else launch_scan(ctx, k_hash_agg_plain<4, false, true>, p, n, true);
-          } else if (no_pf) {
-            if (two) launch_scan(ctx, k_hash_agg_plain<2, false, false>, p, n, false);
-            else launch_scan(ctx, k_hash_agg_plain<4, false, false>, p, n, false);
-          } else {
-            if (two) launch_scan(ctx, k_hash_agg_plain<2, true, false>, p, n, false);
-            else launch_scan(ctx, k_hash_agg_plain<4, true, false>, p, n, false);
-          }
-        } else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
-        else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
-        else if (d <= 4) launch_hash_agg<4>(ctx, p, n, front);
-        else launch_hash_agg<8>(ctx, p, n, front);
+        // tables that outgrow L2: several passes over the rows, each confined to one contiguous part of the table
+        const int npass = (list || front || ranges[ri].second < (4ll << 20) || st->aos) ? 1 : st->npass;
+        p.npass = npass;
+        p.pass_shift = 64;
+        for (int q = 1; q < npass; q <<= 1) p.pass_shift--;
+        const long long max_groups = p.max_groups;
+        for (int pass = 0; pass < npass; pass++) {
+          p.pass_id = pass;
+          p.max_groups = max_groups;
+          if (p.ps.has_nulls) launch_scan(ctx, k_hash_agg<8, false, true>, p, n, false);
+          else if (lean_mask && !list && !front && !st->aos && (p.row_begin & 1) == 0) {
+            // the lean kernel addresses the hybrid layout directly
+            p.lean.key_col = (const unsigned long long*)p.ps.cols[p.plain.key_slot[0]].ptr;
+            p.lean.arg_col = (const unsigned long long*)p.ps.cols[p.plain.arg_slot[0]].ptr;
+            p.lean.min_w = p.lean.max_w = 0;
+            p.lean.sum_arr = p.lean.cnt_arr = nullptr;
+            for (int a = 0; a < st->naggs; a++) {
+              const int f = st->descs[size_t(a)].func, l = st->t.loc[a];
+              if (f == DFGPU_AGG_MIN) p.lean.min_w = l;
+              else if (f == DFGPU_AGG_MAX) p.lean.max_w = l;
+              else if (f == DFGPU_AGG_SUM) p.lean.sum_arr = st->t.add + (long long)(~l) * st->t.astride;
+              else p.lean.cnt_arr = st->t.add + (long long)(~l) * st->t.astride;
+            }
+            bool layout_ok = st->t.lw == (((lean_mask & 3) == 3) ? 4 : ((lean_mask & 3) ? 2 : 1));
+            for (int a = 0; a < st->naggs; a++) {
+              const int f = st->descs[size_t(a)].func;
+              layout_ok = layout_ok && ((f == DFGPU_AGG_MIN || f == DFGPU_AGG_MAX) ? st->t.loc[a] >= 1 : st->t.loc[a] < 0);
+            }
+            if (layout_ok) launch_lean(ctx, p, n, lean_mask, lean_mt);
+            else launch_scan(ctx, k_hash_agg_plain<2, false, false>, p, n, false);
+          } else if (use_plain && !list && (p.row_begin & 1) == 0) {
+            static const bool pf = getenv("DFGPU_AGG_PREFETCH") && atoi(getenv("DFGPU_AGG_PREFETCH")) != 0;  // A/B switch (measured: no gain)
+            const bool two = p.plain.ncols <= 2;
+            if (front) {
+              if (two) launch_scan(ctx, k_hash_agg_plain<2, false, true>, p, n, true);
+              else launch_scan(ctx, k_hash_agg_plain<4, false, true>, p, n, true);
+            } else if (!pf) {
+              if (two) launch_scan(ctx, k_hash_agg_plain<2, false, false>, p, n, false);
+              else launch_scan(ctx, k_hash_agg_plain<4, false, false>, p, n, false);
+            } else {
+              if (two) launch_scan(ctx, k_hash_agg_plain<2, true, false>, p, n, false);
+              else launch_scan(ctx, k_hash_agg_plain<4, true, false>, p, n, false);
+            }
+          } else if (d <= 1) launch_hash_agg<1>(ctx, p, n, front);
+          else if (d <= 2) launch_hash_agg<2>(ctx, p, n, front);
+          else if (d <= 4) launch_hash_agg<4>(ctx, p, n, front);
+          else launch_hash_agg<8>(ctx, p, n, front);
+        }
         unsigned long long c[8];
         read_counters(st, c);
         if (c[3] == 2) fail(DFGPU_ERR_INTERNAL, "front-table merge could not find a slot");
@@ -1762,6 +2269,7 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
         long long want_cap = std::max(AG_MIN_CAP, next_pow2(est * 2));
         while (want_cap > st->cap && want_cap > afford) want_cap >>= 1;
         const bool to_aos = !st->aos && want_aos(est, st->descs, st->naggs);
+        st->npass = (st->aos || to_aos) ? 1 : passes_for(est, st->descs, st->naggs);
         if (to_aos || want_cap > st->cap) {
           st->aos = st->aos || to_aos;
           table_grow(st, std::max(st->cap, want_cap));
@@ -2105,11 +2613,28 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     cp.nkeys = st->nkeys;
     cp.naggs = st->naggs;
     cp.raw = 0;
+    cp.wide_kw = st->wide ? st->nkeys : 0;
+    for (int k = 0; k < st->nkeys && st->wide; k++) cp.key_is_utf8[k] = st->key_is_utf8[size_t(k)];
     dfgpu_result hidden;  // RAII: hash-key and representative columns of a Utf8-keyed aggregate
     hidden.ctx = ctx;
+    std::vector<std::pair<int, size_t>> wide_refs;  // wide keys: (key part, index of its reference column in `hidden`)
     for (int k = 0; k < st->nkeys; k++) {  // group columns first (aggregate.rs:890-925)
       DevColumn c;
       c.dtype = st->key_dtypes[size_t(k)];
+      if (st->wide && st->key_is_utf8[size_t(k)]) {
+        // references to the groups' strings come out of the compaction; the strings are gathered below
+        c.dtype = DFGPU_UINT64;
+        c.values_bytes = alloc_n * 8;
+        c.values = ctx->alloc(c.values_bytes);
+        wide_refs.push_back({k, hidden.cols.size()});
+        hidden.cols.push_back(c);
+        DevColumn u;
+        u.dtype = DFGPU_UTF8;
+        res->cols.push_back(u);
+        cp.out_keys[k] = c.values;
+        cp.key_dtype[k] = DFGPU_UINT64;
+        continue;
+      }
       c.values_bytes = alloc_n * size_t(dtype_width(c.dtype));
       c.values = ctx->alloc(c.values_bytes);
       if (st->utf8_key) {
@@ -2170,6 +2695,8 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       if ((long long)ctx->h_scratch[8] != cnt) fail(DFGPU_ERR_INTERNAL, "table compaction count mismatch");
     }
     res->nrows = cnt;
+    for (auto& wr : wide_refs)  // wide keys: the Utf8 parts' strings, in output order
+      gather_utf8_multi(ctx, st->d_utf8_srcs, (const unsigned long long*)hidden.cols[wr.second].values, cnt, &res->cols[size_t(wr.first)]);
     if (st->utf8_key)  // key strings = the representatives' strings, in output order
       gather_utf8_multi(ctx, st->d_utf8_srcs, (const unsigned long long*)hidden.cols[1].values, cnt, &res->cols[0]);
     if (st->nkeys == 0) {

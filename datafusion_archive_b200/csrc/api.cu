@@ -2,6 +2,9 @@
 // C ABI declared in include/dfgpu.h.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sched.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <memory>
@@ -220,6 +223,50 @@ extern "C" int dfgpu_device_count(int* out) {
   });
 }
 
+// One process (host thread) per GPU: keep that thread and the memory it allocates next — numpy / Arrow buffers,
+// cudaMallocHost staging — on the NUMA node the GPU hangs off.  On the 2-socket B200 hosts GPUs 0-3 sit on node 0
+// and 4-7 on node 1; round 1 measured the 8-rank end-to-end step at 25.6 ms against 15.9 ms for one rank, with
+// ranks and their pinned buffers placed by the OS.  Opt out with DFGPU_NUMA=0.  Best effort: silently does
+// nothing when sysfs does not expose the topology.
+static void bind_to_gpu_numa_node(int device) {
+  if (const char* e = getenv("DFGPU_NUMA")) if (atoi(e) == 0) return;
+  char bus[64] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return; }
+  for (char* c = bus; *c; c++) *c = char(tolower((unsigned char)*c));
+  int node = -1;
+  {
+    FILE* f = fopen((std::string("/sys/bus/pci/devices/") + bus + "/numa_node").c_str(), "r");
+    if (!f) return;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+  }
+  if (node < 0) return;
+  FILE* f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
+  if (!f) return;
+  char list[4096] = {0};
+  const bool got = fgets(list, sizeof(list), f) != nullptr;
+  fclose(f);
+  if (!got) return;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  int ncpu = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k == 1) b = a;
+    if (k < 1) continue;
+    for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); ncpu++; }
+  }
+  if (ncpu == 0) return;
+  sched_setaffinity(0, sizeof(set), &set);
+  // set_mempolicy(MPOL_PREFERRED, {node}): later allocations of this thread come from the GPU's node
+  unsigned long mask[16] = {0};
+  if (node < int(sizeof(mask) * 8)) {
+    mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+    syscall(SYS_set_mempolicy, 1 /*MPOL_PREFERRED*/, mask, sizeof(mask) * 8);
+  }
+}
+
 extern "C" int dfgpu_init(int device, dfgpu_ctx** out) {
   return guarded([&] {
     if (!out) fail(DFGPU_ERR_GENERAL, "dfgpu_init: null out");
@@ -233,6 +280,7 @@ extern "C" int dfgpu_init(int device, dfgpu_ctx** out) {
     auto ctx = std::make_unique<dfgpu_ctx>();
     ctx->device = device;
     ctx->use();
+    bind_to_gpu_numa_node(device);
     cudaDeviceProp prop;
     DF_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
