@@ -1464,7 +1464,7 @@ bool want_aos(long long groups, const std::vector<AggDesc>& descs, int naggs) {
   const long long cap = std::max(AG_MIN_CAP, next_pow2(2 * groups));
   const long long line_hot = std::min(cap * 8 * lw, groups * std::max<long long>(32, 8 * lw));
   const long long arr_hot = std::min(cap * 8, groups * 32);
-  static const long long budget = std::max<long long>(AG_SOA_L2_BUDGET, (long long)env_int("DFGPU_AGG_PASS_MB", 32) * env_int("DFGPU_AGG_MAX_PASSES", 4) << 20);
+  static const long long budget = std::max<long long>(AG_SOA_L2_BUDGET, (long long)env_int("DFGPU_AGG_PASS_MB", 32) * env_int("DFGPU_AGG_MAX_PASSES", 1) << 20);
   return line_hot + n_add * arr_hot > budget;
 }
 
@@ -1569,7 +1569,7 @@ long long hybrid_hot_bytes(long long groups, const std::vector<AggDesc>& descs, 
 int passes_for(long long groups, const std::vector<AggDesc>& descs, int naggs) {
   static const int forced = env_int("DFGPU_AGG_PASSES", 0);          // A/B switch: 1 | 2 | 4 | 8
   static const int pass_mb = env_int("DFGPU_AGG_PASS_MB", 32);       // hot megabytes one pass may touch
-  static const int max_passes = env_int("DFGPU_AGG_MAX_PASSES", 4);
+  static const int max_passes = env_int("DFGPU_AGG_MAX_PASSES", 1);  // measured (profiles/r02d_microbench_agg.txt): a second pass over the input costs what the L2 hits save; off by default
   if (forced > 0) return forced;
   const long long hot = hybrid_hot_bytes(groups, descs, naggs);
   int np = 1;

@@ -137,6 +137,24 @@ def main():
         expp = sort_by_key(O.aggregate([a[keep] for a in arrays], keys, aggs))
         assert np.array_equal(gotp[0], expp[0]) and np.array_equal(gotp[1], expp[1]) and np.array_equal(gotp[4], expp[4])
         np.testing.assert_allclose(gotp[3], expp[3], rtol=1e-9)
+        # the same through the reference-shaped host API: every rank registers the WHOLE table, the
+        # ExecutionContext works on its row range, ctx.sql() returns the global aggregate on every rank
+        from datafusion_archive_b200 import host
+        hctx = host.ExecutionContext(local)
+        uid2 = [engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid2, src=0)
+        hctx.set_partition(rank, world, uid2[0])
+        hctx.register_memory("t", [("k", arrays[0]), ("v", arrays[1])], batch_size=150_000)
+        hk, hmn, hmx, hsm = hctx.sql("SELECT k, MIN(v), MAX(v), SUM(v) FROM t WHERE v < 0.5 GROUP BY k").collect()[0]
+        ho, eo = np.argsort(hk), np.argsort(expp[0])
+        assert np.array_equal(hk[ho], expp[0][eo]) and np.array_equal(hmn[ho], expp[1][eo]) and np.array_equal(hmx[ho], expp[2][eo])
+        np.testing.assert_allclose(hsm[ho], expp[3][eo], rtol=1e-9)
+        hpart = [np.concatenate([b[0] for b in hctx.sql("SELECT v FROM t WHERE v > 0.75").collect()] or [np.zeros(0)])]
+        hg = [None] * world
+        dist.all_gather_object(hg, hpart)
+        # (per-batch row ranges: the concatenation in (batch, rank) order is the global output; compare as multisets per batch boundary-free)
+        assert np.array_equal(np.sort(np.concatenate([g[0] for g in hg])), np.sort(arrays[1][arrays[1] > 0.75]))
+        hctx.close()
         fb = ctx.upload(fmine)
         fpart = ctx.filter_project(fb, fpred, fproj).columns()
         fg = [None] * world

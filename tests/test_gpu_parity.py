@@ -416,11 +416,14 @@ def test_groupby_fused_where_vs_oracle(ctx):
         for nb in [1, 3]:
             got = gpu_agg(ctx, arrays, keys, aggs, nbatches=nb, pred=pred)
             check_groupby(got, exp, 1, exact_cols={0, 1, 2, 4}, sum_cols={3})
-    # expression keys and arguments (interpreter path) under a predicate on another column
+    # expression keys and arguments (interpreter path) under a predicate on another column.  Small: the oracle
+    # restates the reference's per-row re-evaluation of an aggregate's argument expression (aggregate.rs:559),
+    # which is quadratic in the batch size
     rng = np.random.default_rng(77)
-    k = rng.integers(0, 5000, n, dtype=np.int64)
-    w = rng.integers(-100, 100, n, dtype=np.int64)
-    v = rng.random(n)
+    m = 20_000
+    k = rng.integers(0, 500, m, dtype=np.int64)
+    w = rng.integers(-100, 100, m, dtype=np.int64)
+    v = rng.random(m)
     keys2 = [col(0) + lit(7)]
     aggs2 = [AggregateFunction("sum", col(2) * lit(3.0)), AggregateFunction("max", col(1)), AggregateFunction("count", col(2))]
     pred2 = (col(1) > lit(-20)) & (col(2) < lit(0.75))

@@ -139,15 +139,18 @@ def test_wide_table_where_and_pruned_aggregate(ctx):
     rng = np.random.default_rng(9)
     cols = [rng.random(n) - 0.5 if i % 2 == 0 else rng.integers(-9, 9, n, dtype=np.int64) for i in range(20)]
     names = ["c%d" % i for i in range(20)]
-    ctx.register_memory("w", list(zip(names, cols)), batch_size=20_000)
+    reg = lambda: ctx.register_memory("w", list(zip(names, cols)), batch_size=20_000)  # noqa: E731  (data sources are one-pass readers)
+    reg()
     rel = ctx.sql("SELECT c0, c1, c2, c3, c4, c5, c6, c7, c8, c9, c10, c11, c12, c13, c14, c15, c16, c17, c18, c19 FROM w WHERE c2 > 0.1")
     got = rel.collect()
     m = cols[2] > 0.1
     for i in range(20):
         assert np.array_equal(np.concatenate([b[i] for b in got]), cols[i][m]), i
+    reg()
     s, c = ctx.sql("SELECT SUM(c4), COUNT(c4) FROM w WHERE c19 > 0").collect()[0]
     m = cols[19] > 0
     assert c[0] == int(m.sum()) and abs(s[0] - cols[4][m].sum()) <= 1e-9 * abs(cols[4][m].sum())
+    reg()
     k, mx = ctx.sql("SELECT c1, MAX(c18) FROM w WHERE c0 < 0.25 GROUP BY c1").collect()[0]
     m = cols[0] < 0.25
     e = O.aggregate([cols[1][m], cols[18][m]], [col(0)], [AggregateFunction("max", col(1))])
