@@ -81,6 +81,9 @@ def make_col(arr, keepalive):
             c.offsets = bufs[1].address
             c.values = bufs[2].address if bufs[2] is not None else None
             c.values_bytes = bufs[2].size if bufs[2] is not None else 0
+        elif pa.types.is_boolean(arr.type):  # BooleanArray: bit-packed values, LSB first
+            c.dtype = BOOL
+            c.values = bufs[1].address
         else:
             c.dtype = DTYPE_OF_NP[np.dtype(arr.type.to_pandas_dtype())]
             c.values = bufs[1].address
@@ -89,6 +92,11 @@ def make_col(arr, keepalive):
         import pyarrow as pa2
         return make_col(pa2.array(list(arr), type=pa2.string()), keepalive)
     a = np.ascontiguousarray(arr)
+    if a.dtype == np.bool_:  # numpy bools -> arrow BooleanArray layout
+        bits = np.packbits(a, bitorder="little")
+        keepalive.append(bits)
+        c.dtype, c.len, c.offset, c.values = BOOL, a.shape[0], 0, bits.ctypes.data
+        return c
     keepalive.append(a)
     c.dtype = DTYPE_OF_NP[a.dtype]
     c.len = a.shape[0]

@@ -48,6 +48,10 @@ int dtype_width(int dt) {
 
 using namespace dfgpu;
 
+namespace dfgpu {
+void rebase_offsets(dfgpu_ctx* ctx, int* d_off, long long n, int lo);  // utf8_gather.cu
+}
+
 // ---------------------------------------------------------------------------------------------
 // ctx
 // ---------------------------------------------------------------------------------------------
@@ -488,10 +492,12 @@ extern "C" int dfgpu_batch_upload(dfgpu_ctx* ctx, const dfgpu_col* cols, int nco
         h2d(ctx, d.offsets, c.offsets + c.offset, size_t(c.len + 1) * 4);
         const int32_t lo = c.offsets[c.offset], hi = c.offsets[c.offset + c.len];
         if (hi < lo || hi > c.values_bytes) fail(DFGPU_ERR_GENERAL, "corrupt Utf8 offsets");
-        // keep the whole byte buffer prefix so device offsets stay valid as given
-        d.values_bytes = size_t(hi);
+        // only this batch's bytes [lo, hi) travel (a batch is often a slice of a long column: copying the
+        // prefix [0, hi) for every batch is quadratic over a table); the device offsets are rebased by -lo
+        d.values_bytes = size_t(hi - lo);
         d.values = ctx->alloc(d.values_bytes);
-        if (hi > 0) h2d(ctx, d.values, c.values, size_t(hi));
+        if (hi > lo) h2d(ctx, d.values, static_cast<const uint8_t*>(c.values) + lo, size_t(hi - lo));
+        rebase_offsets(ctx, d.offsets, c.len + 1, lo);
       } else {
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("unsupported column type ") + std::to_string(c.dtype));
       }

@@ -125,6 +125,8 @@ __device__ __forceinline__ unsigned long long load_elem(const void* p, int dtype
     case DFGPU_UINT16: return (unsigned long long)__ldg((const unsigned short*)p + row);
     case DFGPU_INT8: return (unsigned long long)(long long)__ldg((const signed char*)p + row);
     case DFGPU_UINT8: return (unsigned long long)__ldg((const unsigned char*)p + row);
+    case DFGPU_BOOL:  // BooleanArray values: bit-packed, LSB first (boolean_ops! operands, expression.rs:212-224)
+      return (unsigned long long)((__ldg((const unsigned char*)p + (row >> 3)) >> (row & 7)) & 1u);
     default: return 0;
   }
 }

@@ -288,7 +288,8 @@ extern "C" int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, co
     FPParams p;
     pb.finish(&p.ps);
     for (int s = 0; s < p.ps.ncols; s++) {
-      if (!is_numeric(p.ps.cols[s].dtype))
+      // Boolean input columns (bit-packed BooleanArray) are read by the direct kernel's interpreter
+      if (!is_numeric(p.ps.cols[s].dtype) && p.ps.cols[s].dtype != DFGPU_BOOL)
         fail(DFGPU_ERR_NOT_IMPLEMENTED, std::string("expressions over ") + dtype_name(p.ps.cols[s].dtype) + " columns are not supported on the GPU path yet");
     }
     if (p.ps.max_depth > 8) fail(DFGPU_ERR_NOT_IMPLEMENTED, "expression too deep (register stack depth > 8)");

@@ -123,6 +123,19 @@ void gather_utf8(dfgpu_ctx* ctx, const DevColumn& src, const unsigned long long*
   ctx->free(d);
 }
 
+// offsets[i] -= lo: a batch that is a slice of a longer Utf8 column uploads only its own bytes [lo, hi)
+__global__ void k_rebase_offsets(int* __restrict__ off, long long n, int lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) off[i] -= lo;
+}
+void rebase_offsets(dfgpu_ctx* ctx, int* d_off, long long n, int lo) {
+  if (n <= 0 || lo == 0) return;
+  long long g = (n + 255) / 256;
+  if (g > 4096) g = 4096;
+  k_rebase_offsets<<<(unsigned)g, 256, 0, ctx->stream>>>(d_off, n, lo);
+  DF_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 void utf8_hash(dfgpu_ctx* ctx, const DevColumn& src, long long n, unsigned long long* d_out) {
   if (n <= 0) return;
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);

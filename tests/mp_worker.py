@@ -149,6 +149,7 @@ def main():
         ho, eo = np.argsort(hk), np.argsort(expp[0])
         assert np.array_equal(hk[ho], expp[0][eo]) and np.array_equal(hmn[ho], expp[1][eo]) and np.array_equal(hmx[ho], expp[2][eo])
         np.testing.assert_allclose(hsm[ho], expp[3][eo], rtol=1e-9)
+        hctx.register_memory("t", [("k", arrays[0]), ("v", arrays[1])], batch_size=150_000)  # data sources are one-pass readers
         hpart = [np.concatenate([b[0] for b in hctx.sql("SELECT v FROM t WHERE v > 0.75").collect()] or [np.zeros(0)])]
         hg = [None] * world
         dist.all_gather_object(hg, hpart)

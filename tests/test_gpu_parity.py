@@ -218,6 +218,49 @@ def test_boolean_projection_outputs(ctx, n):
     assert_cols_bit_equal(gpu_fp(ctx, arrays[:2], pred, proj[:1] + [col(1) >= col(0)]), O.filter_project(arrays[:2], pred, proj[:1] + [col(1) >= col(0)]))
 
 
+def test_boolean_input_columns(ctx):
+    # BooleanArray inputs (bit-packed): boolean_ops! takes any BooleanArray operand (expression.rs:212-224),
+    # a Boolean column can be the whole predicate, be projected, and carry nulls
+    import pyarrow as pa
+    rng = np.random.default_rng(21)
+    for n in [0, 1, 7, 8, 9, 100_003]:
+        a = rng.random(n)
+        f = rng.random(n) < 0.4
+        g = rng.random(n) < 0.7
+        cases = [(col(1), [col(0)]), (col(1) & (col(0) > lit(0.5)), [col(0), col(1)]), ((col(1) | col(2)) & (col(0) < lit(0.9)), [col(2), col(0) * lit(2.0)]),
+                 (None, [col(1) | (col(0) > lit(0.5)), col(1) & col(2)])]
+        for pred, proj in cases:
+            got = gpu_fp(ctx, [a, f, g], pred, proj)
+            O.set_extensions(filter_all_primitives=True)  # FilterRelation gathers every input column; the reference's
+            try:                                          # filter() only knows Float64 / Utf8 (filter.rs:82-108)
+                exp = O.filter_project([a, f, g], pred, proj)
+            finally:
+                O.set_extensions(filter_all_primitives=False)
+            assert len(got) == len(exp)
+            for x, y in zip(got, exp):
+                assert np.array_equal(np.asarray(x), np.asarray(y))
+    # nullable Boolean column next to a nullable Float64 column (arrow 0.12 and / or: null if either side is null)
+    n = 50_000
+    a = rng.random(n)
+    f = rng.random(n) < 0.5
+    fa = pa.array(f, mask=rng.random(n) < 0.2)
+    na = pa.array(a, mask=rng.random(n) < 0.1)
+    O.set_extensions(filter_all_primitives=True)
+    try:
+        for pred, proj in [(col(1) & (col(0) > lit(0.3)), [col(0), col(1)]), (None, [col(1) | (col(0) < lit(0.5))])]:
+            assert_nullable_equal(gpu_fp(ctx, [na, fa], pred, proj), O.filter_project([na, fa], pred, proj))
+    finally:
+        O.set_extensions(filter_all_primitives=False)
+    # fused WHERE with a Boolean column under an aggregate
+    k = rng.integers(0, 50, n, dtype=np.int64)
+    exp = oracle_filtered_aggregate([k, a, f], col(2) & (col(1) < lit(0.8)), [col(0)], [AggregateFunction("max", col(1)), AggregateFunction("count", col(1))])
+    got = gpu_agg(ctx, [k, a, f], [col(0)], [AggregateFunction("max", col(1)), AggregateFunction("count", col(1))], pred=col(2) & (col(1) < lit(0.8)))
+    check_groupby(got, exp, 1, exact_cols={0, 1, 2}, sum_cols=set())
+    with pytest.raises(engine.DfGpuError) as ei:  # aggregate.rs:848-850
+        gpu_agg(ctx, [k, a, f], [col(2)], [AggregateFunction("max", col(1))])
+    assert "Unsupported GROUP BY data type" in str(ei.value)
+
+
 def test_compound_predicates_and_nested_expressions(ctx):
     rng = np.random.default_rng(3)
     a, b, c = rng.random(200_000), rng.random(200_000), rng.random(200_000) + 0.5

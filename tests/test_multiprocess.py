@@ -15,7 +15,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def launch(mode, nproc, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py"), mode]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    if p.returncode != 0:  # keep the workers' own tracebacks (pytest truncates long assertion messages)
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "mp_worker_%s.log" % mode), "w") as f:
+                f.write(p.stdout + "\n---- stderr ----\n" + p.stderr)
+        except OSError:
+            pass
+    return p
 
 
 def test_row_ranges_cover_exactly():
