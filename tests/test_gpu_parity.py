@@ -231,6 +231,9 @@ def test_boolean_input_columns(ctx):
                  (None, [col(1) | (col(0) > lit(0.5)), col(1) & col(2)])]
         for pred, proj in cases:
             got = gpu_fp(ctx, [a, f, g], pred, proj)
+            if n == 0:  # (the oracle's relation yields no batch at all for an empty input)
+                assert all(len(x) == 0 for x in got)
+                continue
             O.set_extensions(filter_all_primitives=True)  # FilterRelation gathers every input column; the reference's
             try:                                          # filter() only knows Float64 / Utf8 (filter.rs:82-108)
                 exp = O.filter_project([a, f, g], pred, proj)
