@@ -37,13 +37,13 @@
 namespace dfgpu {
 
 constexpr int TM_CWARPS = 16;  // consumer warps
-constexpr int TM_SWARPS = 2;   // scan warps (2 x TM_BATCH gathers in flight; 20 warps leave 96 registers per thread)
+constexpr int TM_SWARPS = 2;   // scan warps (2 x TM_BATCH gathers in flight; 20 warps = 5 per SM sub-partition leave 96 registers per thread; a third scan warp was measured: 6 warps on one sub-partition cap the kernel at 80 registers and C2 went from 0.260 to 0.278 ms, profiles/r02_history.md)
 constexpr int TM_BATCH = 4;    // waves per scan-warp batch
 constexpr int TM_WARPS = TM_CWARPS + 2 + TM_SWARPS;
 constexpr int TM_THREADS = TM_WARPS * 32;
 constexpr int TM_MAX_STAGES = 8;
 constexpr int TM_RING = 32;       // slots of the count/offset hand-off rings (> max lag + 1)
-constexpr int TM_MAX_LAG = 16;
+constexpr int TM_MAX_LAG = 24;
 constexpr int TM_MAX_GRID = 160;  // CTAs (= SMs) the wave gather is written for (B200: 148)
 constexpr int TM_HDR_BYTES = 8192;
 constexpr int TM_SMEM_BUDGET = 200 * 1024;
@@ -220,7 +220,7 @@ __device__ __forceinline__ void arith_term_t(const FastOp& t, const unsigned cha
 // FAST: every program of the query is a fast shape, so the interpreter is not even compiled into
 // this instantiation (fewer registers, smaller code).  FAST + F64ONLY: additionally every operand is
 // Float64, and the per-type dispatch of the fast shapes disappears too (the C2 / C3 kernels).
-template <int DEPTH, int K, bool F64ONLY, bool FAST>
+template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false>
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TILE = TM_CWARPS * 32 * K;
@@ -253,15 +253,16 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
 
   if (warp == TM_CWARPS) {
     // ================================ producer A: predicate columns ============================
-    if (p.has_pred) producer_loop(p, TILE, p.col_offA, p.col_offB, ringA, SA, p.stage_bytesA, sh.fullA, sh.emptyA, lane);
+    if (p.has_pred) producer_loop(p, TILE, p.col_offA, STASH ? nullptr : p.col_offB, ringA, SA, p.stage_bytesA, sh.fullA, sh.emptyA, lane);
   } else if (warp == TM_CWARPS + 1) {
     // ================================ producer B: projection columns ===========================
     // Runs as far ahead as ring B allows; the consumers reach these tiles LAG iterations after the
     // predicate pass touched the same rows, so the bytes are L2 hits.
-    if (!p.single_ring) producer_loop(p, TILE, p.col_offB, nullptr, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
+    if (!STASH && !p.single_ring) producer_loop(p, TILE, p.col_offB, nullptr, ringB, SB, p.stage_bytesB, sh.fullB, sh.emptyB, lane);
   } else if (warp >= TM_CWARPS + 2) {
     // ================================ scan warps ================================================
     if (!p.has_pred) return;  // nothing is dropped: output positions are the row numbers
+    if (STASH && p.noscan) return;
     const int sw = warp - (TM_CWARPS + 2);
     int nloc = 0;
     for (int tile = first; tile < p.ntiles; tile += step) nloc++;
@@ -491,11 +492,101 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       if (lane == 0) mbar_arrive(p.single_ring ? &sh.emptyA[s] : &sh.emptyB[s]);
     };
 
+    // ---- stash mode (FAST shapes over 8-byte columns) -----------------------------------------------------
+    // pass 1 of local iteration `it`: predicate, projections, compaction of the selected values into this
+    // tile's slab slot at WARP-LOCAL positions (no global offset needed), stage released at once
+    auto stash1 = [&](int it, int tile, int s, unsigned ph) {
+      mbar_wait(&sh.fullA[s], ph);
+      const unsigned char* stage = ringA + (size_t)s * p.stage_bytesA;
+      const int lrow0 = warp * 32 * K + lane;
+      unsigned valid = KMASK;
+      if (tile == p.ntiles - 1) {  // only the last tile can be ragged
+        const long long row0 = (long long)tile * TILE + lrow0;
+        valid = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if (row0 + k * 32 < p.nrows) valid |= 1u << k;
+      }
+      unsigned flags = cmp_term<K, FAST && F64ONLY>(p.pred_fast.term[0], stage, p.col_offA, lrow0);
+      for (int t = 1; t < p.pred_fast.nterms; t++) {
+        const unsigned ft = cmp_term<K, FAST && F64ONLY>(p.pred_fast.term[t], stage, p.col_offA, lrow0);
+        flags = p.pred_fast.conn[t] ? (flags | ft) : (flags & ft);
+      }
+      flags &= valid;
+      // ranks of this lane's selected rows inside the warp's slice of the tile (row order: k major, lane minor)
+      unsigned pos[K];
+      unsigned run = 0;
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const unsigned m = __ballot_sync(0xffffffffu, (flags >> k) & 1u);
+        pos[k] = run + __popc(m & lt_mask);
+        run += __popc(m);
+      }
+      unsigned long long* slab_w = p.slab + (((size_t)blockIdx.x * p.slab_slots + (size_t)(it % p.slab_slots)) * p.nproj) * TILE + (size_t)warp * 32 * K;
+      for (int q = 0; q < p.nproj; q++) {
+        const FastOp& fo = p.proj_fast[q];
+        unsigned long long v[K];
+        if (fo.kind < 2) {
+          const unsigned long long* A = (const unsigned long long*)(stage + p.col_offA[fo.a]) + lrow0;
+#pragma unroll
+          for (int k = 0; k < K; k++) v[k] = A[k * 32];
+        } else if (F64ONLY || fo.ty == DFGPU_FLOAT64) {
+          double o[K];
+          arith_term_t<K, double>(fo, stage, p.col_offA, lrow0, u2d(fo.imm), flags, bad, o);
+#pragma unroll
+          for (int k = 0; k < K; k++) v[k] = d2u(o[k]);
+        } else {  // Int64 / UInt64: two's complement wrap-around is the natural 64-bit result
+          unsigned long long o[K];
+          arith_term_t<K, unsigned long long>(fo, stage, p.col_offA, lrow0, fo.imm, flags, bad, o);
+#pragma unroll
+          for (int k = 0; k < K; k++) v[k] = o[k];
+        }
+        unsigned long long* dst = slab_w + (size_t)q * TILE;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if ((flags >> k) & 1u) dst[pos[k]] = v[k];
+      }
+      __syncwarp();  // the warp's slab writes are ordered before its later reads (pass 2 runs lanes over other lanes' values)
+      if (lane == 0) {
+        mbar_arrive(&sh.emptyA[s]);
+        sh.s_cnt[it % TM_RING][warp] = run;
+        mbar_arrive(&sh.cnt_ready[it % TM_RING]);
+      }
+      return run;
+    };
+    // pass 2: the warp's `cnt` stashed values go to their final place; coalesced both ways
+    auto stash2 = [&](int it, unsigned cnt) {
+      mbar_wait(&sh.pfx_ready[it % TM_RING], (it / TM_RING) & 1);
+      const unsigned long long base = sh.s_off[it % TM_RING][warp];
+      const unsigned long long* slab_w = p.slab + (((size_t)blockIdx.x * p.slab_slots + (size_t)(it % p.slab_slots)) * p.nproj) * TILE + (size_t)warp * 32 * K;
+      for (int q = 0; q < p.nproj; q++) {
+        const unsigned long long* src = slab_w + (size_t)q * TILE;
+        unsigned long long* dst = (unsigned long long*)p.out[q] + base;
+        unsigned long long v[K];
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if ((unsigned)(k * 32 + lane) < cnt) v[k] = __ldcg(src + k * 32 + lane);
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if ((unsigned)(k * 32 + lane) < cnt) dst[k * 32 + lane] = v[k];
+      }
+    };
+
     int nloc = 0;
     for (int tile = first; tile < p.ntiles; tile += step) nloc++;
     int sb = 0;
     unsigned phb = 0;
-    if (!p.has_pred) {
+    if (STASH) {
+      int sa = 0;
+      unsigned pha = 0;
+      for (int it = 0; it < nloc + LAG; it++) {
+        if (it < nloc) {
+          stash1(it, first + it * step, sa, pha);
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+        if (it >= LAG && !p.noscan) stash2(it - LAG, sh.s_cnt[(it - LAG) % TM_RING][warp]);  // the warp's own count, published LAG tiles ago
+      }
+    } else if (!p.has_pred) {
       // pure projection: no predicate pass, no lag
       for (int it = 0; it < nloc; it++) {
         const int tile = first + it * step;
@@ -512,8 +603,8 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       }
     } else {
       // software pipeline: predicate of tile it, projections of tile it - LAG; the flag bits of the
-      // last LAG+1 tiles live in a 64-bit shift register (K bits per tile)
-      unsigned long long fl = 0;
+      // last LAG+1 tiles live in a 128-bit shift register (K bits per tile: up to 15 tiles of lag at K = 8)
+      unsigned __int128 fl = 0;
       int sa = 0;
       unsigned pha = 0;
       for (int it = 0; it < nloc + LAG; it++) {
@@ -522,7 +613,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
           f0 = phase1(it, first + it * step, sa, pha);
           if (++sa == SA) { sa = 0; pha ^= 1u; }
         }
-        fl = (fl << K) | (unsigned long long)f0;
+        fl = (fl << K) | (unsigned __int128)f0;
         if (it >= LAG) {
           phase2(it - LAG, first + (it - LAG) * step, (unsigned)(fl >> (K * LAG)) & KMASK, sb, phb);
           if (++sb == SB) { sb = 0; phb ^= 1u; }
@@ -533,9 +624,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
   }
 }
 
-template <int DEPTH, int K, bool F64ONLY, bool FAST>
+template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false>
 static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
-  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST>;
+  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST, STASH>;
   if (ctx->first_use((const void*)kern))
     DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 16384 + TM_HDR_BYTES));
   long long grid = std::min(ctx->sm_count, TM_MAX_GRID);  // one persistent CTA per SM
@@ -554,7 +645,9 @@ static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   for (int q = 0; q < p.nproj; q++) fast = fast && p.proj_fast[q].kind > 0;
   bool all_f64 = true;
   for (int c = 0; c < p.ps.ncols; c++) all_f64 = all_f64 && p.ps.cols[c].dtype == DFGPU_FLOAT64;
-  if (fast && all_f64) launch_one<1, K, true, true>(ctx, p, smem);
+  if (p.slab && all_f64) launch_one<1, K, true, true, true>(ctx, p, smem);
+  else if (p.slab) launch_one<1, K, false, true, true>(ctx, p, smem);
+  else if (fast && all_f64) launch_one<1, K, true, true>(ctx, p, smem);
   else if (fast) launch_one<1, K, false, true>(ctx, p, smem);
   else if (p.ps.f64_only) launch_one<DEPTH, K, true, false>(ctx, p, smem);
   else launch_one<DEPTH, K, false, false>(ctx, p, smem);
@@ -589,9 +682,60 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
   int rowU = 0;
   for (int c = 0; c < p.ps.ncols; c++)
     if (inA[c] || inB[c]) rowU += p.col_w[c];
-  const char* mode = getenv("DFGPU_FP_MODE");  // experiment knob: single | dual
+  const char* mode = getenv("DFGPU_FP_MODE");  // experiment knob: single | dual | stash
   int K = 0;
   p.single_ring = 0;
+  p.slab = nullptr;
+  p.slab_slots = 0;
+  p.noscan = getenv("DFGPU_FP_NOSCAN") && atoi(getenv("DFGPU_FP_NOSCAN")) != 0;
+  // stash mode: every program a fast shape over 8-byte columns with 8-byte results
+  // (opt-in, DFGPU_FP_MODE=stash: measured slower than the dual ring at 50 % selectivity, equal at 1 %: profiles/r02m_sweep_fp.txt)
+  bool stash = p.has_pred && p.pred_fast.nterms > 0 && mode && std::string(mode) == "stash";
+  for (int q = 0; stash && q < p.nproj; q++) {
+    const FastOp& fo = p.proj_fast[q];
+    stash = fo.kind > 0 && dtype_width(p.ps.out_dtype[q + p.has_pred]) == 8 &&
+            (fo.kind < 2 || fo.ty == DFGPU_FLOAT64 || fo.ty == DFGPU_INT64 || fo.ty == DFGPU_UINT64);
+  }
+  for (int c = 0; stash && c < p.ps.ncols; c++) stash = !(inA[c] || inB[c]) || p.col_w[c] == 8;
+  if (stash) {
+    for (int k : {8, 4, 2}) {
+      const long long tile = (long long)TM_CWARPS * 32 * k;
+      if (tile * rowU * 3 <= TM_SMEM_BUDGET) { K = k; break; }
+    }
+    if (!K) stash = false;
+  }
+  if (stash) {
+    const int tile = TM_CWARPS * 32 * K;
+    int off = 0;
+    for (int c = 0; c < p.ps.ncols; c++) {
+      p.col_offA[c] = (inA[c] || inB[c]) ? off : -1;
+      p.col_offB[c] = -1;
+      if (inA[c] || inB[c]) off += tile * p.col_w[c];
+    }
+    p.stage_bytesA = off;
+    p.stage_bytesB = 0;
+    p.nstagesA = std::min(TM_MAX_STAGES, TM_SMEM_BUDGET / off);
+    p.nstagesB = 0;
+    const long long grid = std::min(ctx->sm_count, TM_MAX_GRID);
+    // lag: the slab slots the grid keeps live (lag x grid x nproj x tile x 8 bytes, about half of it touched at
+    // 50 % selectivity) should stay L2 resident
+    const long long slot_bytes = grid * p.nproj * (long long)tile * 8;
+    p.lag = (int)std::min<long long>(TM_MAX_LAG, std::max<long long>(TM_BATCH, (96ll << 20) / slot_bytes));
+    if (const char* e = getenv("DFGPU_FP_LAG")) {
+      const int l = atoi(e);
+      if (l >= TM_BATCH - 1 && l <= TM_MAX_LAG) p.lag = l;
+    }
+    p.slab_slots = p.lag + 2;
+    p.slab = (unsigned long long*)ctx->alloc(size_t(grid) * size_t(p.slab_slots) * size_t(slot_bytes / grid));
+    p.ntiles = int((p.nrows + tile - 1) / tile);
+    p.count_ballot = 0;
+    const size_t smem = TM_HDR_BYTES + (size_t)p.nstagesA * p.stage_bytesA;
+    if (K == 8) launch_k<2, 8>(ctx, p, smem);
+    else if (K == 4) launch_k<2, 4>(ctx, p, smem);
+    else launch_k<2, 2>(ctx, p, smem);
+    ctx->free(p.slab);  // stream ordered: the block is only handed out again to work queued behind this kernel
+    return true;
+  }
   if (p.has_pred && mode && std::string(mode) == "single") {  // measured slower than dual on B200 (profiles/r01_history.md): opt-in only
     for (int k : {8, 4, 2}) {
       if (k == 8 && p.ps.max_depth > 2) continue;
@@ -656,11 +800,11 @@ bool launch_fp_tma(dfgpu_ctx* ctx, FPParams& p) {
     if (p.has_pred) {
       const long long l2_budget = 40ll << 20;
       const long long per_tile = (long long)std::min(ctx->sm_count, TM_MAX_GRID) * offB;
-      p.lag = (int)std::min<long long>(std::min(TM_MAX_LAG, 64 / K - 1), std::max<long long>(4, l2_budget / per_tile));
+      p.lag = (int)std::min<long long>(std::min(TM_MAX_LAG, 128 / K - 1), std::max<long long>(4, l2_budget / per_tile));
     }
     if (const char* e = getenv("DFGPU_FP_LAG")) {  // experiment knob
       const int l = atoi(e);
-      if (p.has_pred && l >= TM_BATCH - 1 && l <= std::min(TM_MAX_LAG, 64 / K - 1)) p.lag = l;
+      if (p.has_pred && l >= TM_BATCH - 1 && l <= std::min(TM_MAX_LAG, 128 / K - 1)) p.lag = l;
     }
   }
   p.ntiles = int((p.nrows + tile - 1) / tile);
