@@ -1124,6 +1124,7 @@ struct CompactParams {
   int sentinel_used;
   int nkeys, naggs, raw;
   long long raw_stride;  // raw output: element idx of every raw array lives at idx * raw_stride (0 = 1: dense arrays)
+  const unsigned long long* sentinel_flag;  // non-null: device flag that says whether the sentinel slot (slot cap) is in use
   int wide_kw;           // wide keys: line words 1..wide_kw are the key parts (a Utf8 part = a string reference)
   int key_is_utf8[kMaxKeys];
   AggDesc aggs[kMaxAggs];
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(256) k_compact(const __grid_constant__ Compact
     bool occ = false;
     unsigned long long key = 0;
     if (s < p.cap) { key = *p.t.key(s); occ = key != EMPTY_KEY; }
-    else if (s == p.cap) { key = EMPTY_KEY; occ = p.sentinel_used != 0; }
+    else if (s == p.cap) { key = EMPTY_KEY; occ = p.sentinel_used != 0 || (p.sentinel_flag && *p.sentinel_flag != 0ull); }
     const unsigned m = __ballot_sync(0xffffffffu, occ);
     if (!m) continue;
     unsigned long long basei = 0;
@@ -2536,16 +2537,15 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     k_merge<<<grid_for(ctx, mp.n, 256, 8), 256, 0, ctx->stream>>>(mp);
     DF_CUDA(cudaGetLastError());
     ctx->launches++;
-    unsigned long long c[8];
-    read_counters(st, c);
-    if (c[3]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed");
-    n_owned = (long long)c[0] + (c[2] ? 1 : 0);
-    d_owned = dalloc(size_t(n_owned) * E);
+    // compact what this rank owns without a host round trip in between: room for every received entry, the
+    // sentinel slot's use and the final count stay on the device until the size exchange below
+    d_owned = dalloc(total_recv * E);
     CompactParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.t = ot;
     cp.cap = ocap;
-    cp.sentinel_used = c[2] ? 1 : 0;
+    cp.sentinel_used = 0;
+    cp.sentinel_flag = st->d_counters + 2;
     cp.nkeys = st->nkeys;
     cp.naggs = st->naggs;
     cp.raw = 1;
@@ -2560,15 +2560,23 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     k_compact<<<grid_for(ctx, ocap + 1, 256, 8), 256, 0, ctx->stream>>>(cp);
     DF_CUDA(cudaGetLastError());
     ctx->launches++;
+  } else {
+    DF_CUDA(cudaMemsetAsync(st->d_counters, 0, 64, ctx->stream));
   }
-  // 7. every rank gathers the owned segments (sizes first)
-  unsigned long long* d_n = dalloc(size_t(1 + W));
-  ctx->h_scratch[16] = (unsigned long long)n_owned;
-  DF_CUDA(cudaMemcpyAsync(d_n, ctx->h_scratch + 16, 8, cudaMemcpyHostToDevice, ctx->stream));
-  comm_allgather_u64(ctx, d_n, d_n + 1, 1);
-  std::vector<unsigned long long> owned_n(size_t(W), 0);
-  DF_CUDA(cudaMemcpyAsync(owned_n.data(), d_n + 1, size_t(W) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  // 7. every rank gathers the owned segments: sizes first ([owned entries, merge error flag] per rank)
+  unsigned long long* d_n = dalloc(size_t(2 + 2 * W));
+  DF_CUDA(cudaMemcpyAsync(d_n, st->d_counters + 4, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  DF_CUDA(cudaMemcpyAsync(d_n + 1, st->d_counters + 3, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  comm_allgather_u64(ctx, d_n, d_n + 2, 2);
+  std::vector<unsigned long long> owned_n2(size_t(2 * W), 0);
+  DF_CUDA(cudaMemcpyAsync(owned_n2.data(), d_n + 2, size_t(2 * W) * 8, cudaMemcpyDeviceToHost, ctx->stream));
   DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<unsigned long long> owned_n(size_t(W), 0);
+  for (int r = 0; r < W; r++) {
+    if (owned_n2[size_t(2 * r + 1)]) fail(DFGPU_ERR_INTERNAL, "partial-aggregate merge failed on rank " + std::to_string(r));
+    owned_n[size_t(r)] = owned_n2[size_t(2 * r)];
+  }
+  n_owned = (long long)owned_n[size_t(me)];
   std::vector<size_t> g_off(size_t(W), 0), g_cnt(size_t(W), 0);
   size_t G = 0;
   for (int r = 0; r < W; r++) {
