@@ -1263,6 +1263,11 @@ __global__ void __launch_bounds__(256) k_owner_scatter(const __grid_constant__ O
 struct DecodeParams {
   const unsigned long long* rows;
   long long n;
+  // rows arrive as `nseg` segments of seg_stride entries each, of which the first seg_n[r] are real (the padded
+  // all-gather of the owned groups); nseg == 0: one dense list
+  int nseg;
+  long long seg_stride;
+  long long seg_n[AG_MAX_WORLD];
   int nkeys, naggs;
   AggDesc aggs[kMaxAggs];
   unsigned long long key_mask[kMaxKeys];
@@ -1274,7 +1279,14 @@ struct DecodeParams {
 __global__ void __launch_bounds__(256) k_decode_rows(const __grid_constant__ DecodeParams p) {
   const long long E = 1 + p.naggs;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const unsigned long long* row = p.rows + i * E;
+    long long at = i;
+    if (p.nseg) {  // dense output index -> (segment, entry)
+      long long j = i;
+      int r = 0;
+      while (r < p.nseg - 1 && j >= p.seg_n[r]) j -= p.seg_n[r++];
+      at = (long long)r * p.seg_stride + j;
+    }
+    const unsigned long long* row = p.rows + at * E;
     const unsigned long long key = row[0];
     for (int k = 0; k < p.nkeys; k++) store_elem(p.out_keys[k], p.key_dtype[k], i, (key >> p.key_shift[k]) & p.key_mask[k]);
     for (int a = 0; a < p.naggs; a++) {
@@ -2393,7 +2405,12 @@ void agg_exchange_scalars(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
 
 // GROUP BY.  Returns the global result as raw rows of (1 + naggs) words in *rows (caller frees) and their number.
 constexpr int HDR = 16;  // header words: [0] typed [1] nkeys [2] naggs [3] utf8 [4] rows_seen [5] key dtypes (8 bits each) [6] arg dtypes (8 bits each)
-void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long** rows_out, long long* n_out) {
+struct GatheredSegments {
+  int nseg = 0;
+  long long stride = 0;
+  long long n[AG_MAX_WORLD] = {0};
+};
+void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long** rows_out, long long* n_out, GatheredSegments* seg) {
   const int W = ctx->world, me = ctx->rank;
   if (W > AG_MAX_WORLD) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than " + std::to_string(AG_MAX_WORLD) + " ranks");
   Trace tr(ctx);
@@ -2497,6 +2514,12 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     total_recv += cnt(r, me);
   }
   if ((long long)total_send != n_local) fail(DFGPU_ERR_INTERNAL, "owner counts do not add up to the local groups");
+  size_t max_recv = 1;  // the most entries any rank receives (column sums of the count matrix)
+  for (int r = 0; r < W; r++) {
+    size_t col = 0;
+    for (int q = 0; q < W; q++) col += cnt(q, r);
+    max_recv = std::max(max_recv, col);
+  }
   unsigned long long* d_send = dalloc(total_send * E);
   if (n_local > 0) {
     unsigned long long* d_cursor = dalloc(size_t(W));
@@ -2537,9 +2560,10 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     k_merge<<<grid_for(ctx, mp.n, 256, 8), 256, 0, ctx->stream>>>(mp);
     DF_CUDA(cudaGetLastError());
     ctx->launches++;
-    // compact what this rank owns without a host round trip in between: room for every received entry, the
-    // sentinel slot's use and the final count stay on the device until the size exchange below
-    d_owned = dalloc(total_recv * E);
+    // compact what this rank owns without a host round trip in between: the buffer has room for the largest
+    // number of entries any rank receives (known to all from the count matrix), which also makes it a valid send
+    // buffer of the padded all-gather below; the sentinel slot's use and the count stay on the device
+    d_owned = dalloc(max_recv * E);
     CompactParams cp;
     memset(&cp, 0, sizeof(cp));
     cp.t = ot;
@@ -2577,19 +2601,26 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     owned_n[size_t(r)] = owned_n2[size_t(2 * r)];
   }
   n_owned = (long long)owned_n[size_t(me)];
-  std::vector<size_t> g_off(size_t(W), 0), g_cnt(size_t(W), 0);
-  size_t G = 0;
+  // one fixed-size all-gather of max_owned entries per rank (owners are a hash of the key, so the segments are
+  // within a few percent of each other): one collective instead of one broadcast per rank
+  size_t max_owned = 0, G = 0;
   for (int r = 0; r < W; r++) {
-    g_off[size_t(r)] = G * E;
-    g_cnt[size_t(r)] = size_t(owned_n[size_t(r)]) * E;
+    max_owned = std::max(max_owned, size_t(owned_n[size_t(r)]));
     G += size_t(owned_n[size_t(r)]);
   }
-  unsigned long long* d_final = (unsigned long long*)ctx->alloc((G ? G * E : 1) * 8);
-  comm_allgather_v(ctx, d_owned, d_final, g_off.data(), g_cnt.data());
+  if (max_owned > max_recv) fail(DFGPU_ERR_INTERNAL, "owned groups exceed the received entries");
+  unsigned long long* d_final = (unsigned long long*)ctx->alloc((max_owned ? size_t(W) * max_owned * E : 1) * 8);
+  if (max_owned > 0) {
+    if (!d_owned) d_owned = dalloc(max_recv * E);  // a rank that owns nothing still contributes its (empty) segment
+    comm_allgather_u64(ctx, d_owned, d_final, max_owned * E);
+  }
   DF_CUDA(cudaStreamSynchronize(ctx->stream));  // the temporaries above are released on return
   tr.mark("exchange: owner merge + gather");
   *rows_out = d_final;
   *n_out = (long long)G;
+  seg->nseg = W;
+  seg->stride = (long long)max_owned;
+  for (int r = 0; r < W; r++) seg->n[r] = (long long)owned_n[size_t(r)];
 }
 
 }  // namespace
@@ -2624,10 +2655,11 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     // multi-GPU: every rank must take part (also one that saw no batch), and every rank gets the global result
     unsigned long long* xrows = nullptr;
     long long xn = -1;
+    GatheredSegments xseg;
     struct XFree { dfgpu_ctx* c; unsigned long long** p; ~XFree() { c->free(*p); } } xfree{ctx, &xrows};
     if (ctx->world > 1) {
       if (st->nkeys == 0) agg_exchange_scalars(ctx, st);
-      else agg_exchange_groups(ctx, st, &xrows, &xn);
+      else agg_exchange_groups(ctx, st, &xrows, &xn, &xseg);
     }
     auto res = std::make_unique<dfgpu_result>();
     res->ctx = ctx;
@@ -2694,6 +2726,9 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
       memset(&dp, 0, sizeof(dp));
       dp.rows = xrows;
       dp.n = xn;
+      dp.nseg = xseg.nseg;
+      dp.seg_stride = xseg.stride;
+      for (int r = 0; r < xseg.nseg; r++) dp.seg_n[r] = xseg.n[r];
       dp.nkeys = st->nkeys;
       dp.naggs = st->naggs;
       for (int k = 0; k < st->nkeys; k++) {

@@ -244,7 +244,10 @@ static void bind_to_gpu_numa_node(int device) {
     if (fscanf(f, "%d", &node) != 1) node = -1;
     fclose(f);
   }
-  if (node < 0) return;
+  if (node < 0) {
+    if (getenv("DFGPU_TRACE")) fprintf(stderr, "[dfgpu trace] device %d (%s): sysfs reports no NUMA node\n", device, bus);
+    return;
+  }
   FILE* f = fopen(("/sys/devices/system/node/node" + std::to_string(node) + "/cpulist").c_str(), "r");
   if (!f) return;
   char list[4096] = {0};
@@ -262,7 +265,8 @@ static void bind_to_gpu_numa_node(int device) {
     for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); ncpu++; }
   }
   if (ncpu == 0) return;
-  sched_setaffinity(0, sizeof(set), &set);
+  const int rc_aff = sched_setaffinity(0, sizeof(set), &set);
+  if (getenv("DFGPU_TRACE")) fprintf(stderr, "[dfgpu trace] device %d (%s) -> NUMA node %d, %d cpus, sched_setaffinity rc=%d\n", device, bus, node, ncpu, rc_aff);
   // set_mempolicy(MPOL_PREFERRED, {node}): later allocations of this thread come from the GPU's node
   unsigned long mask[16] = {0};
   if (node < int(sizeof(mask) * 8)) {
