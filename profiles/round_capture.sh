@@ -14,8 +14,12 @@ for w in c2 c3 c4 c5 reduce; do
   k=k_filter_project; [ $w = c4 ] && k=k_hash_agg; [ $w = c5 ] && k=k_hash_agg; [ $w = reduce ] && k=k_reduce
   # c4 / c5: the second k_hash_agg launch of an operator pass is the bulk scan (the first is the 1 Mi-row prefix)
   skip=2; [ $w = c4 ] && skip=3; [ $w = c5 ] && skip=3
-  timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o $out/${tag}_$w python profiles/run_kernels.py $w > /dev/null 2>&1
+  timeout 200 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o /tmp/${tag}_$w python profiles/run_kernels.py $w > /dev/null 2>&1
+  # summaries are made here: gpurun only brings back 64 MiB and one report is ~20 MiB
+  python profiles/summarize.py /tmp/${tag}_$w.ncu-rep $out/${tag}_$w.summary.txt > /dev/null 2>&1
+  python profiles/srcstat.py /tmp/${tag}_$w.ncu-rep 25 > $out/${tag}_$w.lines.txt 2>&1
 done
+cp /tmp/${tag}_c2.ncu-rep $out/ 2>/dev/null  # one raw report for auditing the summaries
 timeout 120 python profiles/microbench_fp.py > $out/${tag}_microbench_fp.txt 2>&1
 timeout 200 python profiles/microbench_agg.py > $out/${tag}_microbench_agg.txt 2>&1
 ./profiles/bin/scatter_ops2 > $out/${tag}_scatter_ops2.txt 2>&1
