@@ -317,7 +317,7 @@ def run_ours(args):
     ms, kms, kn, launches = time_steps(ctx, torch, step_resident, steps, warmup)
     assert state["nrows"] == n_sel, "GPU row count %d != expected %d" % (state["nrows"], n_sel)
     # sustained: the same step back to back for >= 0.5 s (same kernel, clocks sampled throughout)
-    sus_steps = max(steps, int(np.ceil(600.0 / max(ms / steps, 1e-3))))
+    sus_steps = steps if args.no_sustained else max(steps, int(np.ceil(600.0 / max(ms / steps, 1e-3))))
     sms, skms, skn, _ = time_steps(ctx, torch, step_resident, sus_steps, 0)
     clocks = sampler.stop()
     total_rows = sum_over_ranks(torch, float(n))
@@ -545,6 +545,7 @@ def main():
     ap.add_argument("--rows", type=int, default=100_000_000, help="rows per GPU")
     ap.add_argument("--rows5", type=int, default=0, help="rows per GPU of the C5 extra (default 1.25 x --rows)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-sustained", action="store_true", help="keep the sustained loop as short as the timed steps (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
