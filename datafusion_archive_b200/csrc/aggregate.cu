@@ -15,6 +15,7 @@
 namespace dfgpu {
 
 void utf8_hash(dfgpu_ctx* ctx, const DevColumn& src, long long n, unsigned long long* d_out);
+void shift_copy_i32(dfgpu_ctx* ctx, int* dst, const int* src, long long n, int add);
 void gather_utf8_multi(dfgpu_ctx* ctx, const Utf8Source* d_srcs, const unsigned long long* d_idx, long long nsel, DevColumn* out);
 
 constexpr int AG_THREADS = 256;
@@ -1818,7 +1819,6 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
     if (ukey) {
       if (st->typed && !st->utf8_key) fail(DFGPU_ERR_GENERAL, "GROUP BY key types changed between batches");
       if (!st->typed && st->naggs >= kMaxAggs) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY key with " + std::to_string(kMaxAggs) + " aggregates");
-      if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys with a multi-GPU communicator");
       if (st->utf8_srcs.size() >= (1u << 20)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than 2^20 batches with a Utf8 GROUP BY key");
       d_hash = (unsigned long long*)ctx->alloc(size_t(batch->nrows > 0 ? batch->nrows : 1) * 8);
       utf8_hash(ctx, *ukey, batch->nrows, d_hash);
@@ -2017,7 +2017,6 @@ void agg_update(dfgpu_aggstate* st, const dfgpu_batch* batch) {
     }
 
     if (st->wide) {
-      if (ctx->world > 1) fail(DFGPU_ERR_NOT_IMPLEMENTED, "composite GROUP BY keys wider than 64 bits or with Utf8 parts under a multi-GPU communicator");
       // retain this batch's Utf8 key columns: a group's string lives in the batch whose row created it
       p.wide.kw = st->nkeys;
       bool new_src = false;
@@ -2410,7 +2409,7 @@ struct GatheredSegments {
   long long stride = 0;
   long long n[AG_MAX_WORLD] = {0};
 };
-void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long** rows_out, long long* n_out, GatheredSegments* seg) {
+void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long** rows_out, long long* n_out, GatheredSegments* seg, bool* regroup) {
   const int W = ctx->world, me = ctx->rank;
   if (W > AG_MAX_WORLD) fail(DFGPU_ERR_NOT_IMPLEMENTED, "more than " + std::to_string(AG_MAX_WORLD) + " ranks");
   Trace tr(ctx);
@@ -2420,7 +2419,10 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
   // 1. local entries, counted per owner
   unsigned long long *keys = nullptr, *vals = nullptr;
   long long n_local = 0;
-  if (st->typed) {
+  // Utf8 and wide keys do not fit the (packed key, accumulators) rows of this exchange: if any rank has them, every
+  // rank leaves through the regroup merge (finish_regroup) right after the header round
+  const bool special = st->typed && (st->wide || st->utf8_key);
+  if (st->typed && !special) {
     agg_export_raw(st, &keys, &vals, &n_local);
     owned.push_back(keys);
     owned.push_back(vals);
@@ -2445,12 +2447,14 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
   memset(hh, 0, HDR * 8);
   hh[0] = st->typed ? 1 : 0;
   hh[1] = (unsigned long long)st->nkeys;
-  hh[2] = (unsigned long long)st->naggs;
-  hh[3] = st->utf8_key ? 1 : 0;
+  hh[2] = (unsigned long long)(st->utf8_key ? st->naggs - 1 : st->naggs);  // user aggregates
+  hh[3] = special ? 1 : 0;
+  hh[7] = st->utf8_key ? 1 : 0;  // the single-Utf8-key form carries a hidden representative aggregate
   hh[4] = (unsigned long long)st->rows_seen;
   if (st->typed) {
     for (int k = 0; k < st->nkeys; k++) hh[5] |= (unsigned long long)(st->key_dtypes[size_t(k)] & 0xff) << (8 * k);
-    for (int a = 0; a < st->naggs; a++) hh[6] |= (unsigned long long)(st->descs[size_t(a)].dtype & 0xff) << (8 * a);
+    for (int a = 0; a < (st->utf8_key ? st->naggs - 1 : st->naggs); a++) hh[6] |= (unsigned long long)(st->descs[size_t(a)].dtype & 0xff) << (8 * a);
+    if (st->utf8_key) hh[5] = DFGPU_UTF8;  // the key the caller sees (internally: a UInt64 string hash)
   }
   DF_CUDA(cudaMemcpyAsync(d_rec, hh, HDR * 8, cudaMemcpyHostToDevice, ctx->stream));
   // 2. all-gather (header, counts)
@@ -2467,10 +2471,10 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
   for (int r = 0; r < W; r++) {
     total_rows += (long long)hdr(r, 4);
     if ((int)hdr(r, 1) != st->nkeys) fail(DFGPU_ERR_GENERAL, "ranks disagree on the GROUP BY expressions");
-    if (hdr(r, 3)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "Utf8 GROUP BY keys with a multi-GPU communicator");
+    if (hdr(r, 3)) *regroup = true;
     if (hdr(r, 0)) {
       if (typed_rank < 0) typed_rank = r;
-      else if (hdr(r, 5) != hdr(typed_rank, 5) || hdr(r, 6) != hdr(typed_rank, 6) || hdr(r, 2) != hdr(typed_rank, 2))
+      else if (hdr(r, 5) != hdr(typed_rank, 5) || hdr(r, 6) != hdr(typed_rank, 6) || hdr(r, 2) != hdr(typed_rank, 2) || hdr(r, 3) != hdr(typed_rank, 3))
         fail(DFGPU_ERR_GENERAL, "ranks disagree on GROUP BY key / aggregate argument types");
     }
   }
@@ -2492,14 +2496,19 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
     st->key_shift.clear();
     st->key_mask.clear();
     int bits = 0;
-    for (int k = st->nkeys - 1; k >= 0; k--) {
+    for (int k = st->nkeys - 1; k >= 0 && !*regroup; k--) {  // (the regroup merge never packs keys)
       const int w = dtype_width(st->key_dtypes[size_t(k)]) * 8;
       st->key_shift.insert(st->key_shift.begin(), bits);
       st->key_mask.insert(st->key_mask.begin(), w == 64 ? ~0ull : ((1ull << w) - 1ull));
       bits += w;
     }
-    if (st->nkeys == 1) st->key_mask[0] = ~0ull;
+    if (st->nkeys == 1 && !*regroup) st->key_mask[0] = ~0ull;
     st->typed = true;
+  }
+  if (*regroup) {
+    *rows_out = nullptr;
+    *n_out = -1;
+    return;
   }
   const size_t E = size_t(1 + st->naggs);
   // 4. scatter the local entries into per-owner segments
@@ -2625,6 +2634,168 @@ void agg_exchange_groups(dfgpu_ctx* ctx, dfgpu_aggstate* st, unsigned long long*
 
 }  // namespace
 
+// Multi-GPU merge for key shapes whose groups cannot travel as (packed key, accumulators) rows — Utf8 keys and
+// wide composite keys: every rank finishes locally, the ranks all-gather their LOCAL RESULT columns (strings
+// included), and every rank aggregates the concatenation once more with the merge function of each aggregate
+// (SUM -> SUM, COUNT -> SUM of counts, MIN -> MIN, MAX -> MAX) through the same single-GPU operator.  O(W x G) work
+// per rank instead of the owner-partitioned O(G): accepted for these shapes.  Results agree across ranks bit for
+// bit except Float64 SUMs (order of the second aggregation's reductions: <= 1e-9 relative).
+namespace {
+struct WorldGuard {  // run a stretch of the operator as if no communicator were attached
+  dfgpu_ctx* c;
+  int world;
+  explicit WorldGuard(dfgpu_ctx* ctx) : c(ctx), world(ctx->world) { c->world = 1; }
+  ~WorldGuard() { c->world = world; }
+};
+
+std::unique_ptr<dfgpu_result> finish_regroup(dfgpu_ctx* ctx, dfgpu_aggstate* st) {
+  const int W = ctx->world, me = ctx->rank;
+  const int user_aggs = st->utf8_key ? st->naggs - 1 : st->naggs;
+  const int ncols = st->nkeys + user_aggs;
+  // 1. this rank's own result (an empty one when it saw no batch: types were adopted from the header)
+  std::unique_ptr<dfgpu_result> local;
+  if (st->t.base) {
+    WorldGuard g(ctx);
+    dfgpu_result* r = nullptr;
+    const int rc = dfgpu_aggregate_finish(st, &r);
+    if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+    local.reset(r);
+  } else {
+    local = std::make_unique<dfgpu_result>();
+    local->ctx = ctx;
+    local->nrows = 0;
+    for (int k = 0; k < st->nkeys; k++) {
+      DevColumn c;
+      c.dtype = st->key_dtypes[size_t(k)];
+      if (c.dtype == DFGPU_UTF8) {
+        c.offsets = (int32_t*)ctx->alloc(4);
+        DF_CUDA(cudaMemsetAsync(c.offsets, 0, 4, ctx->stream));
+      }
+      local->cols.push_back(c);
+    }
+    for (int a = 0; a < user_aggs; a++) {
+      DevColumn c;
+      c.dtype = st->descs[size_t(a)].out_dtype;
+      local->cols.push_back(c);
+    }
+  }
+  if (int(local->cols.size()) != ncols) fail(DFGPU_ERR_INTERNAL, "regroup merge: unexpected local result shape");
+  // 2. sizes: [rows, bytes of every Utf8 column] per rank
+  const int NH = 1 + kMaxKeys;
+  std::vector<void*> tmp;
+  struct Freer { dfgpu_ctx* c; std::vector<void*>* v; ~Freer() { for (void* q : *v) c->free(q); } } freer{ctx, &tmp};
+  auto dalloc = [&](size_t bytes) { void* q = ctx->alloc(bytes ? bytes : 8); tmp.push_back(q); return q; };
+  unsigned long long* d_h = (unsigned long long*)dalloc(size_t(NH) * 8 * size_t(W + 1));
+  unsigned long long* hh = ctx->h_scratch + 16;
+  memset(hh, 0, size_t(NH) * 8);
+  hh[0] = (unsigned long long)local->nrows;
+  for (int k = 0; k < st->nkeys; k++)
+    if (local->cols[size_t(k)].dtype == DFGPU_UTF8) hh[1 + k] = (unsigned long long)local->cols[size_t(k)].values_bytes;
+  DF_CUDA(cudaMemcpyAsync(d_h, hh, size_t(NH) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  comm_allgather_u64(ctx, d_h, d_h + NH, size_t(NH));
+  std::vector<unsigned long long> all(size_t(NH) * size_t(W));
+  DF_CUDA(cudaMemcpyAsync(all.data(), d_h + NH, all.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  long long N = 0;
+  std::vector<long long> row_base(size_t(W), 0);
+  for (int r = 0; r < W; r++) {
+    row_base[size_t(r)] = N;
+    N += (long long)all[size_t(r) * NH];
+  }
+  if (N >= (1ll << 31)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "regroup merge of 2^31 or more partial groups");
+  // 3. gather every result column
+  auto gathered = std::make_unique<dfgpu_batch>();
+  gathered->ctx = ctx;
+  gathered->nrows = N;
+  std::vector<size_t> off(size_t(W), 0), cnt(size_t(W), 0);
+  for (int c = 0; c < ncols; c++) {
+    const DevColumn& lc = local->cols[size_t(c)];
+    DevColumn gc;
+    gc.dtype = lc.dtype;
+    if (lc.dtype == DFGPU_UTF8) {
+      // bytes
+      size_t total_b = 0;
+      std::vector<size_t> bbase(size_t(W), 0);
+      for (int r = 0; r < W; r++) {
+        bbase[size_t(r)] = total_b;
+        off[size_t(r)] = total_b;
+        cnt[size_t(r)] = size_t(all[size_t(r) * NH + 1 + size_t(c)]);
+        total_b += cnt[size_t(r)];
+      }
+      if (total_b >= (1ull << 31)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "regroup merge of 2 GiB or more of key strings");
+      gc.values_bytes = total_b;
+      gc.values = ctx->alloc(total_b ? total_b : 1);
+      comm_allgather_bytes_v(ctx, lc.values, gc.values, off.data(), cnt.data());
+      // offsets: every rank's (rows + 1) array, spliced with its byte base
+      int* raw = (int*)dalloc(size_t(N + W) * 4);
+      for (int r = 0; r < W; r++) {
+        off[size_t(r)] = size_t(row_base[size_t(r)] + r) * 4;
+        cnt[size_t(r)] = size_t(all[size_t(r) * NH] + 1) * 4;
+      }
+      comm_allgather_bytes_v(ctx, lc.offsets, raw, off.data(), cnt.data());
+      gc.offsets = (int32_t*)ctx->alloc(size_t(N + 1) * 4);
+      for (int r = 0; r < W; r++)
+        shift_copy_i32(ctx, gc.offsets + row_base[size_t(r)], raw + row_base[size_t(r)] + r, (long long)all[size_t(r) * NH], int(bbase[size_t(r)]));
+      const int last = int(total_b);
+      DF_CUDA(cudaMemcpyAsync(gc.offsets + N, &last, 4, cudaMemcpyHostToDevice, ctx->stream));
+      DF_CUDA(cudaStreamSynchronize(ctx->stream));  // `last` is a stack variable
+    } else {
+      const size_t w = size_t(dtype_width(lc.dtype));
+      for (int r = 0; r < W; r++) {
+        off[size_t(r)] = size_t(row_base[size_t(r)]) * w;
+        cnt[size_t(r)] = size_t(all[size_t(r) * NH]) * w;
+      }
+      gc.values_bytes = size_t(N) * w;
+      gc.values = ctx->alloc(gc.values_bytes ? gc.values_bytes : 8);
+      comm_allgather_bytes_v(ctx, lc.values, gc.values, off.data(), cnt.data());
+    }
+    gathered->cols.push_back(gc);
+  }
+  DF_CUDA(cudaStreamSynchronize(ctx->stream));
+  (void)me;
+  // 4. aggregate the partial results once more, with each aggregate's merge function
+  const size_t nk = size_t(st->nkeys), na = size_t(user_aggs);
+  std::vector<dfgpu_insn> kprog(nk), aprog(na);
+  std::vector<const dfgpu_insn*> kptr;
+  std::vector<int> klen;
+  for (int k = 0; k < st->nkeys; k++) {
+    memset(&kprog[size_t(k)], 0, sizeof(dfgpu_insn));
+    kprog[size_t(k)].op = DFGPU_OP_COL;
+    kprog[size_t(k)].col = k;
+    kprog[size_t(k)].dtype = gathered->cols[size_t(k)].dtype;
+    kptr.push_back(&kprog[size_t(k)]);
+    klen.push_back(1);
+  }
+  std::vector<dfgpu_agg> aggs(na);
+  for (int a = 0; a < user_aggs; a++) {
+    memset(&aprog[size_t(a)], 0, sizeof(dfgpu_insn));
+    aprog[size_t(a)].op = DFGPU_OP_COL;
+    aprog[size_t(a)].col = st->nkeys + a;
+    aprog[size_t(a)].dtype = gathered->cols[size_t(st->nkeys + a)].dtype;
+    const int f = st->descs[size_t(a)].func;
+    aggs[size_t(a)].func = f == DFGPU_AGG_COUNT ? DFGPU_AGG_SUM : f;
+    aggs[size_t(a)].arg = &aprog[size_t(a)];
+    aggs[size_t(a)].arg_len = 1;
+    aggs[size_t(a)].out_dtype = gathered->cols[size_t(st->nkeys + a)].dtype;
+    aggs[size_t(a)]._pad = 0;
+  }
+  WorldGuard g(ctx);
+  dfgpu_aggstate* st2 = nullptr;
+  int rc = dfgpu_aggregate_create(ctx, kptr.data(), klen.data(), st->nkeys, aggs.data(), user_aggs, N / W + 1, &st2);
+  if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+  struct StFree { dfgpu_aggstate* s; ~StFree() { dfgpu_aggregate_free(s); } } stfree{st2};
+  dfgpu_result* res = nullptr;
+  if (N > 0) {
+    rc = dfgpu_aggregate_update(st2, gathered.get());
+    if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+    rc = dfgpu_aggregate_finish(st2, &res);
+    if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+    return std::unique_ptr<dfgpu_result>(res);
+  }
+  return local;  // nobody had a group: the (empty) local result has the right columns
+}
+}  // namespace
+
 extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
   return guarded([&] {
     if (!st || !out) fail(DFGPU_ERR_GENERAL, "dfgpu_aggregate_finish: null argument");
@@ -2656,10 +2827,16 @@ extern "C" int dfgpu_aggregate_finish(dfgpu_aggstate* st, dfgpu_result** out) {
     unsigned long long* xrows = nullptr;
     long long xn = -1;
     GatheredSegments xseg;
+    bool regroup = false;
     struct XFree { dfgpu_ctx* c; unsigned long long** p; ~XFree() { c->free(*p); } } xfree{ctx, &xrows};
     if (ctx->world > 1) {
       if (st->nkeys == 0) agg_exchange_scalars(ctx, st);
-      else agg_exchange_groups(ctx, st, &xrows, &xn, &xseg);
+      else agg_exchange_groups(ctx, st, &xrows, &xn, &xseg, &regroup);
+      if (regroup) {
+        *out = finish_regroup(ctx, st).release();
+        st->finished = true;
+        return;
+      }
     }
     auto res = std::make_unique<dfgpu_result>();
     res->ctx = ctx;

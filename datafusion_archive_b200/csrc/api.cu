@@ -732,6 +732,21 @@ void comm_allgather_v(dfgpu_ctx* ctx, const unsigned long long* send, unsigned l
   DF_NCCL(N.GroupEnd());
 }
 
+// byte-granular all-gather of segments of different sizes (one grouped ncclBroadcast per root): the regroup merge of
+// Utf8 / wide-key aggregates ships whole result columns
+void comm_allgather_bytes_v(dfgpu_ctx* ctx, const void* send, void* recv, const size_t* off, const size_t* cnt) {
+  NcclApi& N = nccl();
+  ncclComm_t comm = comm_of(ctx);
+  const int W = ctx->world, me = ctx->rank;
+  DF_NCCL(N.GroupStart());
+  for (int r = 0; r < W; r++) {
+    if (!cnt[r]) continue;
+    char* dst = static_cast<char*>(recv) + off[r];
+    DF_NCCL(N.Broadcast(r == me ? send : (const void*)dst, dst, cnt[r], ncclInt8, r, comm, ctx->stream));
+  }
+  DF_NCCL(N.GroupEnd());
+}
+
 void comm_allreduce_aggs(dfgpu_ctx* ctx, int naggs, const int* funcs, const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull,
                          unsigned long long* d_rows /* [1] rows seen, summed */) {
   NcclApi& N = nccl();

@@ -135,6 +135,7 @@ void comm_allgather_u64(dfgpu_ctx* ctx, const unsigned long long* send, unsigned
 void comm_exchange_v(dfgpu_ctx* ctx, const unsigned long long* send, const size_t* send_off, const size_t* send_cnt,
                      unsigned long long* recv, const size_t* recv_off, const size_t* recv_cnt);
 void comm_allgather_v(dfgpu_ctx* ctx, const unsigned long long* send, unsigned long long* recv, const size_t* off, const size_t* cnt);
+void comm_allgather_bytes_v(dfgpu_ctx* ctx, const void* send, void* recv, const size_t* off, const size_t* cnt);
 void comm_allreduce_aggs(dfgpu_ctx* ctx, int naggs, const int* funcs, const int* mtypes, unsigned long long* d_vals, unsigned long long* d_nonnull,
                          unsigned long long* d_rows);
 // one Utf8 column on the device (arrow 0.12 BinaryArray): the unit of the multi-source string gather

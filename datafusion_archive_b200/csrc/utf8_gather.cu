@@ -136,6 +136,19 @@ void rebase_offsets(dfgpu_ctx* ctx, int* d_off, long long n, int lo) {
   ctx->launches++;
 }
 
+// dst[i] = src[i] + add: splices one rank's offsets array into the concatenated Utf8 column of the regroup merge
+__global__ void k_shift_copy_i32(int* __restrict__ dst, const int* __restrict__ src, long long n, int add) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i] + add;
+}
+void shift_copy_i32(dfgpu_ctx* ctx, int* dst, const int* src, long long n, int add) {
+  if (n <= 0) return;
+  long long g = (n + 255) / 256;
+  if (g > 4096) g = 4096;
+  k_shift_copy_i32<<<(unsigned)g, 256, 0, ctx->stream>>>(dst, src, n, add);
+  DF_CUDA(cudaGetLastError());
+  ctx->launches++;
+}
+
 void utf8_hash(dfgpu_ctx* ctx, const DevColumn& src, long long n, unsigned long long* d_out) {
   if (n <= 0) return;
   const int grid = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);

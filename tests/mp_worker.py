@@ -156,6 +156,52 @@ def main():
         # (per-batch row ranges: the concatenation in (batch, rank) order is the global output; compare as multisets per batch boundary-free)
         assert np.array_equal(np.sort(np.concatenate([g[0] for g in hg])), np.sort(arrays[1][arrays[1] > 0.75]))
         hctx.close()
+        # key shapes that do not travel as packed 64-bit keys — wide composites and Utf8 — merge by regrouping the
+        # gathered local results (aggregate.cu finish_regroup); every rank ends with the global result
+        rng = np.random.default_rng(99)
+        wn = 120_000
+        wk1 = workloads.mix_keys(rng.integers(0, 200, wn, dtype=np.int64))
+        wk2 = rng.integers(-(2 ** 62), 2 ** 62, 30, dtype=np.int64)[rng.integers(0, 30, wn)]
+        wk3 = rng.integers(0, 5, wn, dtype=np.int32)
+        vocab = ["", "a", "ab", "London, UK", "y" * 40] + ["s%03d" % i for i in range(50)]
+        ws = [vocab[i] for i in rng.integers(0, len(vocab), wn)]
+        wv = rng.random(wn)
+        wi = rng.integers(-9, 9, wn, dtype=np.int64)
+
+        def wide_aggs(cv, ci):
+            return [AggregateFunction("min", col(cv)), AggregateFunction("max", col(cv)), AggregateFunction("sum", col(ci)),
+                    AggregateFunction("count", col(cv)), AggregateFunction("sum", col(cv))]
+
+        def rows(cols, nk):
+            cols = [c if isinstance(c, list) else c.tolist() for c in cols]
+            return sorted(zip(*cols), key=lambda r: r[:nk])
+
+        wlo, whi = parallel.row_range(rank, world, wn)
+        for cols_, wkeys, cv, ci, schema in [([wk1, wk2, wv, wi], [col(0), col(1)], 2, 3, [A.INT64, A.INT64, A.FLOAT64, A.INT64]),
+                                             ([ws, wv, wi], [col(0)], 1, 2, [A.UTF8, A.FLOAT64, A.INT64]),
+                                             ([ws, wk3, wv, wi], [col(0), col(1)], 2, 3, [A.UTF8, A.INT32, A.FLOAT64, A.INT64])]:
+            nk = len(wkeys)
+            wa = wide_aggs(cv, ci)
+            wexp = rows(O.aggregate(cols_, wkeys, wa), nk)
+            wb = ctx.upload([c[wlo:whi] for c in cols_])
+            for variant in ("all ranks", "rank 1 empty"):
+                if variant == "all ranks":
+                    wgot = rows(ctx.aggregate(wb, wkeys, wa).columns(), nk)
+                    want = wexp
+                else:
+                    wgot = rows(aggregate_maybe_empty(ctx, engine, wb if rank != 1 else None, schema, wkeys, wa), nk)
+                    keep_rows = np.ones(wn, dtype=bool)
+                    l1, h1 = parallel.row_range(1, world, wn)
+                    keep_rows[l1:h1] = False
+                    sel = [([x for x, k in zip(c, keep_rows) if k] if isinstance(c, list) else c[keep_rows]) for c in cols_]
+                    want = rows(O.aggregate(sel, wkeys, wa), nk)
+                assert len(wgot) == len(want), (variant, nk, len(wgot), len(want))
+                for rg, re_ in zip(wgot, want):
+                    for i, (x, y) in enumerate(zip(rg, re_)):
+                        if i == nk + 4:
+                            assert x == y or abs(x - y) <= 1e-9 * abs(y), (variant, rg, re_)
+                        else:
+                            assert x == y, (variant, rg, re_)
         fb = ctx.upload(fmine)
         fpart = ctx.filter_project(fb, fpred, fproj).columns()
         fg = [None] * world
