@@ -75,6 +75,23 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
       "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(TM_WAIT_HINT_NS)
       : "memory");
 }
+// the same on 32-bit shared-window addresses kept in registers (the lean consumer loop: no generic -> shared
+// conversion, S2UR SR_CgaCtaId + ULEA, in front of every barrier operation)
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity), "r"(TM_WAIT_HINT_NS)
+      : "memory");
+}
 // 1-D bulk async copy global -> shared, completion reported to an mbarrier (TMA engine; UBLKCP),
 // with an L2 eviction-priority hint: the predicate stream marks bytes that the projection stream
 // will re-read LAG tiles later as evict_last; the projection stream (and bytes read once) use
@@ -217,10 +234,238 @@ __device__ __forceinline__ void arith_term_t(const FastOp& t, const unsigned cha
   }
 }
 
+// ---- lean consumer loop ---------------------------------------------------------------------------
+// The shapes the headline configurations have (C2: SELECT a WHERE a > c; C3: SELECT a+b, a*b WHERE b < a): ONE
+// Float64 comparison as the predicate and one or two projections that copy an 8-byte column or combine Float64
+// operands.  ncu on the generic FAST loop (profiles/r02_c2.lines.txt, SASS view in profiles/r02_history.md): 383
+// instructions per warp-tile of which ~120 touch rows; the rest re-derives per-tile invariants — indexed
+// constant-bank loads of the column offsets behind the term's column index, a jump table on the comparison
+// operator, generic -> shared address conversions in front of every mbarrier operation — and its dependent
+// latencies (short scoreboard 19 %, no-instruction 7 %, branch resolving 5 % of the consumer samples) are what the
+// 4 consumer warps per scheduler cannot hide.  Here the comparison operator and the operand kind are template
+// parameters, every offset, pointer and barrier address is computed once before the loop, and the loop body is
+// waits + loads + compares + the ballot-compacted store.  Protocol (barriers, rings, scan warps) unchanged.
+template <int CMP>
+__device__ __forceinline__ bool lean_cmp(double a, double b) {
+  if (CMP == V_EQ) return a == b;
+  if (CMP == V_NE) return a != b;
+  if (CMP == V_LT) return a < b;
+  if (CMP == V_LE) return a <= b;
+  if (CMP == V_GT) return a > b;
+  return a >= b;
+}
+
+// predicated 8-byte store (the compiler turns `if (selected) out[pos] = v` into a divergent branch per row when the
+// value's load can be sunk into it; the compacted store wants @P STG)
+__device__ __forceinline__ void st_if(unsigned cond, unsigned long long* dst, unsigned long long v) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %0, 0;\n"
+      "@p st.global.b64 [%1], %2;\n"
+      "}\n" ::"r"(cond), "l"(dst), "l"(v)
+      : "memory");
+}
+
+// 8-byte load from a 32-bit shared-window address (ordered with the mbarrier operations around it: volatile + memory)
+__device__ __forceinline__ unsigned long long lds64(unsigned addr) {
+  unsigned long long v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// One row slot of the ballot compaction, fused: p = (flags & bit) != 0; m = ballot(p); pos = run + popc(m & lanes
+// below); @p store v at o[pos]; run += popc(m).  One predicate feeds the vote and the store (the C++ form costs a
+// shift + and + compare for the vote and an and + compare again for the store).
+__device__ __forceinline__ unsigned compact_store(unsigned flags, unsigned bit, unsigned lt_mask, unsigned& run, unsigned long long* o, unsigned long long v) {
+  unsigned pos;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 m, t;\n"
+      ".reg .b64 a;\n"
+      "and.b32 t, %2, %3;\n"
+      "setp.ne.u32 p, t, 0;\n"
+      "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+      "and.b32 t, m, %4;\n"
+      "popc.b32 t, t;\n"
+      "add.u32 %1, t, %0;\n"
+      "mad.wide.u32 a, %1, 8, %5;\n"
+      "@p st.global.b64 [a], %6;\n"
+      "popc.b32 m, m;\n"
+      "add.u32 %0, %0, m;\n"
+      "}\n"
+      : "+r"(run), "=&r"(pos)
+      : "r"(flags), "r"(bit), "r"(lt_mask), "l"(o), "l"(v)
+      : "memory");
+  return pos;
+}
+
+constexpr int LEAN_MAX_PROJ = 2;
+
+template <int K, int CMP, bool PB, int NP>
+__device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int lane) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];  // the kernel's dynamic shared memory: 32-bit shared-window arithmetic below
+  TmaShared& sh = *reinterpret_cast<TmaShared*>(smem_raw);
+  constexpr int TILE = TM_CWARPS * 32 * K;
+  constexpr unsigned KMASK = (1u << K) - 1u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int nloc = first < p.ntiles ? (p.ntiles - first + step - 1) / step : 0;
+  const int SA = p.nstagesA, SB = p.nstagesB, LAG = p.lag;
+  const bool single = p.single_ring != 0;
+  const int last_it = (p.ntiles - 1 - first) % step == 0 ? (p.ntiles - 1 - first) / step : -1;  // the only ragged tile, if this CTA owns it
+  unsigned sh0 = smem_u32(smem_raw);
+  asm volatile("" : "+r"(sh0));  // one register for every barrier address: do not re-derive the shared-window base at every use
+  constexpr unsigned b_fullA = (unsigned)offsetof(TmaShared, fullA), b_emptyA = (unsigned)offsetof(TmaShared, emptyA);
+  constexpr unsigned b_fullB = (unsigned)offsetof(TmaShared, fullB), b_emptyB = (unsigned)offsetof(TmaShared, emptyB);
+  constexpr unsigned b_cnt = (unsigned)offsetof(TmaShared, cnt_ready), b_pfx = (unsigned)offsetof(TmaShared, pfx_ready);
+  // operand offsets (bytes from the start of shared memory) in stage 0
+  const int lrow0 = warp * 32 * K + lane;
+  const FastOp& pt = p.pred_fast.term[0];
+  const double pimm = u2d(pt.imm);
+  const int ringA_off = TM_HDR_BYTES, stageA = p.stage_bytesA;
+  const int ring2_off = single ? TM_HDR_BYTES : TM_HDR_BYTES + SA * stageA;
+  const int stage2 = single ? stageA : p.stage_bytesB;
+  const unsigned a1 = sh0 + (unsigned)(ringA_off + p.col_offA[pt.a] + lrow0 * 8);  // shared-window addresses: LDS [R + imm], nothing to derive per tile
+  const unsigned b1 = PB ? sh0 + (unsigned)(ringA_off + p.col_offA[pt.b] + lrow0 * 8) : a1;
+  unsigned a2[NP], b2[NP];
+  int kop2[NP];
+  double imm2[NP];
+  unsigned long long* out2[NP];
+#pragma unroll
+  for (int q = 0; q < NP; q++) {
+    const FastOp& fo = p.proj_fast[q];
+    kop2[q] = fo.kind == 1 ? -1 : (fo.kind == 2 ? fo.op : fo.op | 0x100);  // -1 copy; op (+0x100: the right operand is the immediate)
+    imm2[q] = u2d(fo.imm);
+    a2[q] = sh0 + (unsigned)(ring2_off + p.col_offB[fo.a] + lrow0 * 8);
+    b2[q] = fo.kind == 2 ? sh0 + (unsigned)(ring2_off + p.col_offB[fo.b] + lrow0 * 8) : a2[q];
+    out2[q] = (unsigned long long*)p.out[q];
+  }
+  bool bad = false;
+  unsigned __int128 fl = 0;  // flag bits of the last LAG+1 tiles, K per tile
+  int sa = 0, sb = 0;
+  unsigned pha = 0, phb = 0;
+  for (int it = 0; it < nloc + LAG; it++) {
+    unsigned f0 = 0;
+    if (it < nloc) {
+      // ---- predicate of tile `it` -> K flag bits, the warp's count to the scan warp
+      mbar_wait_a(sh0 + b_fullA + 8u * sa, pha);
+      const unsigned A = a1 + (unsigned)(sa * stageA), B = b1 + (unsigned)(sa * stageA);
+      double x[K], y[K];
+#pragma unroll
+      for (int k = 0; k < K; k++) x[k] = u2d(lds64(A + k * 256));
+#pragma unroll
+      for (int k = 0; k < K; k++) y[k] = PB ? u2d(lds64(B + k * 256)) : pimm;
+#pragma unroll
+      for (int k = 0; k < K; k++) f0 |= (unsigned)lean_cmp<CMP>(x[k], y[k]) << k;
+      if (it == last_it) {
+        const long long row0 = ((long long)first + (long long)it * step) * TILE + lrow0;
+        unsigned valid = 0;
+#pragma unroll
+        for (int k = 0; k < K; k++)
+          if (row0 + k * 32 < p.nrows) valid |= 1u << k;
+        f0 &= valid;
+      }
+      const unsigned cnt = __reduce_add_sync(0xffffffffu, (unsigned)__popc(f0));
+      if (lane == 0) {
+        if (!single) mbar_arrive_a(sh0 + b_emptyA + 8u * sa);  // this warp is done reading the stage
+        sh.s_cnt[it % TM_RING][warp] = cnt;
+        mbar_arrive_a(sh0 + b_cnt + 8u * (it % TM_RING));
+      }
+      if (++sa == SA) { sa = 0; pha ^= 1u; }
+    }
+    fl = (fl << K) | (unsigned __int128)f0;
+    if (it >= LAG) {
+      // ---- projections of tile it - LAG: selected rows go to their compacted global position
+      const int j = it - LAG;
+      const unsigned flags = (unsigned)(fl >> (K * LAG)) & KMASK;
+      mbar_wait_a(sh0 + b_pfx + 8u * (j % TM_RING), (j / TM_RING) & 1);
+      const unsigned long long base = sh.s_off[j % TM_RING][warp];
+      if (!single) mbar_wait_a(sh0 + b_fullB + 8u * sb, phb);
+      // projection values of the K rows of this lane, then the ballot compaction: the rank of a selected row inside the
+      // warp's slice (row order: k major, lane minor) is computed while the first projection is stored
+      unsigned pos[K];
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const unsigned A = a2[q] + (unsigned)(sb * stage2);
+        unsigned long long* o = out2[q] + base;
+        unsigned long long v[K];
+        if (kop2[q] < 0) {
+#pragma unroll
+          for (int k = 0; k < K; k++) v[k] = lds64(A + k * 256);
+        } else {
+          const unsigned B = b2[q] + (unsigned)(sb * stage2);
+          const bool rimm = (kop2[q] & 0x100) != 0;
+          const int op = kop2[q] & 0xff;
+          double x[K], y[K];
+#pragma unroll
+          for (int k = 0; k < K; k++) x[k] = u2d(lds64(A + k * 256));
+#pragma unroll
+          for (int k = 0; k < K; k++) y[k] = rimm ? imm2[q] : u2d(lds64(B + k * 256));
+          if (op == V_ADD) {
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = x[k] + y[k];
+          } else if (op == V_MUL) {
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = x[k] * y[k];
+          } else if (op == V_SUB) {
+#pragma unroll
+            for (int k = 0; k < K; k++) x[k] = x[k] - y[k];
+          } else {  // V_DIV
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+              if (y[k] == 0.0 && (flags & (1u << k))) bad = true;  // DivideByZero on a surviving row
+              x[k] = x[k] / y[k];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < K; k++) v[k] = d2u(x[k]);
+        }
+        if (q == 0) {
+          unsigned run = 0;
+#pragma unroll
+          for (int k = 0; k < K; k++) pos[k] = compact_store(flags, 1u << k, lt_mask, run, o, v[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < K; k++) st_if(flags & (1u << k), o + pos[k], v[k]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive_a(sh0 + (single ? b_emptyA : b_emptyB) + 8u * sb);
+      if (++sb == SB) { sb = 0; phb ^= 1u; }
+    }
+  }
+  if (bad) *p.err_flag = 1u;
+}
+
+template <int K, int NP>
+__device__ __forceinline__ void consumer_lean_dispatch(const FPParams& p, int warp, int lane) {
+  const int op = p.pred_fast.term[0].op;
+  const bool pb = p.pred_fast.term[0].kind == 2;
+#define DF_LEAN(OP)                                            \
+  case OP:                                                     \
+    if (pb) consumer_lean<K, OP, true, NP>(p, warp, lane);     \
+    else consumer_lean<K, OP, false, NP>(p, warp, lane);       \
+    break;
+  switch (op) {
+    DF_LEAN(V_EQ)
+    DF_LEAN(V_NE)
+    DF_LEAN(V_LT)
+    DF_LEAN(V_LE)
+    DF_LEAN(V_GT)
+    default:
+      if (pb) consumer_lean<K, V_GE, true, NP>(p, warp, lane);
+      else consumer_lean<K, V_GE, false, NP>(p, warp, lane);
+      break;
+  }
+#undef DF_LEAN
+}
+
 // FAST: every program of the query is a fast shape, so the interpreter is not even compiled into
 // this instantiation (fewer registers, smaller code).  FAST + F64ONLY: additionally every operand is
 // Float64, and the per-type dispatch of the fast shapes disappears too (the C2 / C3 kernels).
-template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false>
+template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false, int LEAN = 0>  // LEAN = number of projections of a lean shape
 __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __grid_constant__ FPParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int TILE = TM_CWARPS * 32 * K;
@@ -347,6 +592,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         for (int i = 0; i < nb; i++) mbar_arrive(&sh.pfx_ready[(w0 + i) % TM_RING]);
       }
     }
+  } else if constexpr (LEAN > 0) {
+    // ================================ consumer warps, lean shapes ================================
+    consumer_lean_dispatch<K, LEAN>(p, warp, lane);
   } else {
     // ================================ consumer warps ============================================
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -624,9 +872,9 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
   }
 }
 
-template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false>
+template <int DEPTH, int K, bool F64ONLY, bool FAST, bool STASH = false, int LEAN = 0>
 static void launch_one(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
-  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST, STASH>;
+  auto kern = k_filter_project_tma<DEPTH, K, F64ONLY, FAST, STASH, LEAN>;
   if (ctx->first_use((const void*)kern))
     DF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TM_SMEM_BUDGET + 16384 + TM_HDR_BYTES));
   long long grid = std::min(ctx->sm_count, TM_MAX_GRID);  // one persistent CTA per SM
@@ -645,7 +893,12 @@ static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   for (int q = 0; q < p.nproj; q++) fast = fast && p.proj_fast[q].kind > 0;
   bool all_f64 = true;
   for (int c = 0; c < p.ps.ncols; c++) all_f64 = all_f64 && p.ps.cols[c].dtype == DFGPU_FLOAT64;
-  if (p.slab && all_f64) launch_one<1, K, true, true, true>(ctx, p, smem);
+  // lean shapes: one Float64 comparison, one or two copy / arithmetic projections (DFGPU_FP_LEAN=0: A/B switch)
+  bool lean = fast && all_f64 && p.has_pred && p.pred_fast.nterms == 1 && p.nproj >= 1 && p.nproj <= LEAN_MAX_PROJ && !p.slab && !p.count_ballot;
+  if (const char* e = getenv("DFGPU_FP_LEAN")) lean = lean && atoi(e) != 0;
+  if (lean && p.nproj == 1) launch_one<1, K, true, true, false, 1>(ctx, p, smem);
+  else if (lean) launch_one<1, K, true, true, false, 2>(ctx, p, smem);
+  else if (p.slab && all_f64) launch_one<1, K, true, true, true>(ctx, p, smem);
   else if (p.slab) launch_one<1, K, false, true, true>(ctx, p, smem);
   else if (fast && all_f64) launch_one<1, K, true, true>(ctx, p, smem);
   else if (fast) launch_one<1, K, false, true>(ctx, p, smem);

@@ -12,8 +12,11 @@ which = sys.argv[1] if len(sys.argv) > 1 else "c2"
 n = int(float(sys.argv[2])) if len(sys.argv) > 2 else 100_000_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 ctx = engine.GpuContext(0)
-if which in ("c2", "c3"):
-    arrays, pred, proj = (workloads.c2 if which == "c2" else workloads.c3)(n)
+if which in ("c2", "c3", "sel1"):
+    arrays, pred, proj = (workloads.c3 if which == "c3" else workloads.c2)(n)
+    if which == "sel1":  # 1 % selectivity: the predicate pass alone
+        from datafusion_archive_b200.expr import col, lit
+        pred = col(0) > lit(0.99)
     b = ctx.upload(arrays)
     for _ in range(reps):
         r = ctx.filter_project(b, pred, proj)

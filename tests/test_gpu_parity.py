@@ -311,6 +311,40 @@ def test_all_numeric_dtypes(ctx, np_dt):
         assert_cols_bit_equal(got, exp)
 
 
+def test_lean_filter_shapes_all_operators(ctx):
+    # the lean consumer loop of k_filter_project_tma is instantiated per comparison operator and operand kind
+    # (column / literal) for one or two copy / arithmetic projections: every instantiation against the oracle,
+    # NaN, +-0, infinities and a zero divisor among the rows, tile-ragged sizes
+    rng = np.random.default_rng(77)
+    for n in [4095, 70_001]:
+        a = rng.random(n)
+        b = rng.random(n)
+        special = np.array([np.nan, 0.0, -0.0, np.inf, -np.inf, 5e-324, 0.5])
+        a[rng.integers(0, n, 300)] = special[rng.integers(0, len(special), 300)]
+        b[rng.integers(0, n, 300)] = special[rng.integers(0, len(special), 300)]
+        b[::7] = a[::7]  # equal pairs
+        preds = []
+        for rhs in (col(1), lit(0.5)):
+            preds += [col(0) < rhs, col(0) <= rhs, col(0) > rhs, col(0) >= rhs, col(0).eq(rhs), col(0).not_eq(rhs)]
+        projs = [[col(0)], [col(1), col(0)], [col(0) + col(1), col(0) * col(1)], [col(0) - col(1)], [col(1) * lit(3.0), col(0) - lit(0.25)],
+                 [col(0) + lit(1.0)]]
+        for i, p in enumerate(preds):
+            pr = projs[i % len(projs)]
+            assert_cols_bit_equal(gpu_fp(ctx, [a, b], p, pr), O.filter_project([a, b], p, pr))
+        # division: fine while no surviving row divides by zero; DivideByZero otherwise (like the generic path)
+        d = np.where(b == 0.0, 1.0, b)
+        assert_cols_bit_equal(gpu_fp(ctx, [a, d], col(0) > lit(0.25), [col(0) / col(1)]), O.filter_project([a, d], col(0) > lit(0.25), [col(0) / col(1)]))
+        assert_cols_bit_equal(gpu_fp(ctx, [a, d], col(0) > lit(0.25), [col(0) / lit(4.0), col(1)]), O.filter_project([a, d], col(0) > lit(0.25), [col(0) / lit(4.0), col(1)]))
+        z = d.copy()
+        z[n // 2] = 0.0
+        a2 = a.copy()
+        a2[n // 2] = 0.75  # the row survives the filter
+        with pytest.raises(Exception):
+            gpu_fp(ctx, [a2, z], col(0) > lit(0.25), [col(0) / col(1)])
+        a2[n // 2] = 0.1   # filtered out: no error
+        assert_cols_bit_equal(gpu_fp(ctx, [a2, z], col(0) > lit(0.25), [col(0) / col(1)]), O.filter_project([a2, z], col(0) > lit(0.25), [col(0) / col(1)]))
+
+
 def test_nan_and_signed_zero_compare(ctx):
     a = np.array([np.nan, 0.0, -0.0, 1.0, -np.inf, np.inf, np.nan, 5e-324] * 100)
     b = np.roll(a, 3)
