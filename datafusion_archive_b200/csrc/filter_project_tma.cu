@@ -38,7 +38,10 @@ namespace dfgpu {
 
 constexpr int TM_CWARPS = 16;  // consumer warps
 constexpr int TM_SWARPS = 2;   // scan warps (2 x TM_BATCH gathers in flight; 20 warps = 5 per SM sub-partition leave 96 registers per thread; a third scan warp was measured: 6 warps on one sub-partition cap the kernel at 80 registers and C2 went from 0.260 to 0.278 ms, profiles/r02_history.md)
-constexpr int TM_BATCH = 4;    // waves per scan-warp batch
+#ifndef DF_TM_BATCH
+#define DF_TM_BATCH 4
+#endif
+constexpr int TM_BATCH = DF_TM_BATCH;  // waves per scan-warp batch.  Measured with the lean consumer loop (profiles/r02x_sweep_fp_scan_variants.txt): 2 -> C2 0.298 ms, 3 -> 0.260, 4 -> 0.239; issuing a wave's gather right behind its own publish: 0.33-0.41
 constexpr int TM_WARPS = TM_CWARPS + 2 + TM_SWARPS;
 constexpr int TM_THREADS = TM_WARPS * 32;
 constexpr int TM_MAX_STAGES = 8;
@@ -519,6 +522,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
       unsigned excl[TM_BATCH];
       unsigned long long total[TM_BATCH];
       // 1. per-tile counts -> exclusive per-warp offsets, publish the tile totals
+      unsigned long long sv[TM_BATCH][TM_MAX_GRID / 32];
 #pragma unroll
       for (int i = 0; i < TM_BATCH; i++) {
         excl[i] = 0;
@@ -539,7 +543,6 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_filter_project_tma(const __gr
         }
       }
       // 2. gather the counts of every tile of these waves: all loads issued before any is used
-      unsigned long long sv[TM_BATCH][TM_MAX_GRID / 32];
 #pragma unroll
       for (int i = 0; i < TM_BATCH; i++) {
         const long long wave0 = (long long)(w0 + i) * step;
