@@ -41,7 +41,7 @@ constexpr int TM_SWARPS = 2;   // scan warps (2 x TM_BATCH gathers in flight; 20
 #ifndef DF_TM_BATCH
 #define DF_TM_BATCH 4
 #endif
-constexpr int TM_BATCH = DF_TM_BATCH;  // waves per scan-warp batch.  Measured with the lean consumer loop (profiles/r02x_sweep_fp_scan_variants.txt): 2 -> C2 0.298 ms, 3 -> 0.260, 4 -> 0.239; issuing a wave's gather right behind its own publish: 0.33-0.41
+constexpr int TM_BATCH = DF_TM_BATCH;  // waves per scan-warp batch.  Measured with the lean consumer loop (profiles/r02x_sweep_fp_scan_variants.txt): 2 -> C2 0.298 ms, 3 -> 0.260, 4 -> 0.239; issuing a wave's gather right behind its own publish: 0.33-0.41; one wave per step with the gather consumed a step later (profiles/r02z_sweep_fp_scan_pipe2.txt): 0.38 at every lag (statuses read right after the publish are stale and the re-poll is serial)
 constexpr int TM_WARPS = TM_CWARPS + 2 + TM_SWARPS;
 constexpr int TM_THREADS = TM_WARPS * 32;
 constexpr int TM_MAX_STAGES = 8;
@@ -248,14 +248,21 @@ __device__ __forceinline__ void arith_term_t(const FastOp& t, const unsigned cha
 // 4 consumer warps per scheduler cannot hide.  Here the comparison operator and the operand kind are template
 // parameters, every offset, pointer and barrier address is computed once before the loop, and the loop body is
 // waits + loads + compares + the ballot-compacted store.  Protocol (barriers, rings, scan warps) unchanged.
-template <int CMP>
-__device__ __forceinline__ bool lean_cmp(double a, double b) {
+template <int CMP, class T>
+__device__ __forceinline__ bool lean_cmp_t(T a, T b) {
   if (CMP == V_EQ) return a == b;
   if (CMP == V_NE) return a != b;
   if (CMP == V_LT) return a < b;
   if (CMP == V_LE) return a <= b;
   if (CMP == V_GT) return a > b;
   return a >= b;
+}
+// TY: 0 = Float64, 1 = Int64, 2 = UInt64 (operands as raw 8-byte words)
+template <int CMP, int TY>
+__device__ __forceinline__ bool lean_cmp(unsigned long long a, unsigned long long b) {
+  if (TY == 0) return lean_cmp_t<CMP, double>(u2d(a), u2d(b));
+  if (TY == 1) return lean_cmp_t<CMP, long long>((long long)a, (long long)b);
+  return lean_cmp_t<CMP, unsigned long long>(a, b);
 }
 
 // predicated 8-byte store (the compiler turns `if (selected) out[pos] = v` into a divergent branch per row when the
@@ -306,7 +313,7 @@ __device__ __forceinline__ unsigned compact_store(unsigned flags, unsigned bit, 
 
 constexpr int LEAN_MAX_PROJ = 2;
 
-template <int K, int CMP, bool PB, int NP>
+template <int K, int CMP, bool PB, int NP, int TY>
 __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int lane) {
   extern __shared__ __align__(128) unsigned char smem_raw[];  // the kernel's dynamic shared memory: 32-bit shared-window arithmetic below
   TmaShared& sh = *reinterpret_cast<TmaShared*>(smem_raw);
@@ -326,7 +333,7 @@ __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int l
   // operand offsets (bytes from the start of shared memory) in stage 0
   const int lrow0 = warp * 32 * K + lane;
   const FastOp& pt = p.pred_fast.term[0];
-  const double pimm = u2d(pt.imm);
+  const unsigned long long pimm = pt.imm;
   const int ringA_off = TM_HDR_BYTES, stageA = p.stage_bytesA;
   const int ring2_off = single ? TM_HDR_BYTES : TM_HDR_BYTES + SA * stageA;
   const int stage2 = single ? stageA : p.stage_bytesB;
@@ -334,13 +341,14 @@ __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int l
   const unsigned b1 = PB ? sh0 + (unsigned)(ringA_off + p.col_offA[pt.b] + lrow0 * 8) : a1;
   unsigned a2[NP], b2[NP];
   int kop2[NP];
-  double imm2[NP];
+  unsigned long long imm2[NP];
   unsigned long long* out2[NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) {
     const FastOp& fo = p.proj_fast[q];
-    kop2[q] = fo.kind == 1 ? -1 : (fo.kind == 2 ? fo.op : fo.op | 0x100);  // -1 copy; op (+0x100: the right operand is the immediate)
-    imm2[q] = u2d(fo.imm);
+    // -1 copy; op (+0x100: the right operand is the immediate; +0x200: 64-bit integer arithmetic, two's complement wrap-around)
+    kop2[q] = fo.kind == 1 ? -1 : ((fo.kind == 2 ? fo.op : fo.op | 0x100) | (fo.ty == DFGPU_FLOAT64 ? 0 : 0x200));
+    imm2[q] = fo.imm;
     a2[q] = sh0 + (unsigned)(ring2_off + p.col_offB[fo.a] + lrow0 * 8);
     b2[q] = fo.kind == 2 ? sh0 + (unsigned)(ring2_off + p.col_offB[fo.b] + lrow0 * 8) : a2[q];
     out2[q] = (unsigned long long*)p.out[q];
@@ -355,13 +363,13 @@ __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int l
       // ---- predicate of tile `it` -> K flag bits, the warp's count to the scan warp
       mbar_wait_a(sh0 + b_fullA + 8u * sa, pha);
       const unsigned A = a1 + (unsigned)(sa * stageA), B = b1 + (unsigned)(sa * stageA);
-      double x[K], y[K];
+      unsigned long long x[K], y[K];
 #pragma unroll
-      for (int k = 0; k < K; k++) x[k] = u2d(lds64(A + k * 256));
+      for (int k = 0; k < K; k++) x[k] = lds64(A + k * 256);
 #pragma unroll
-      for (int k = 0; k < K; k++) y[k] = PB ? u2d(lds64(B + k * 256)) : pimm;
+      for (int k = 0; k < K; k++) y[k] = PB ? lds64(B + k * 256) : pimm;
 #pragma unroll
-      for (int k = 0; k < K; k++) f0 |= (unsigned)lean_cmp<CMP>(x[k], y[k]) << k;
+      for (int k = 0; k < K; k++) f0 |= (unsigned)lean_cmp<CMP, TY>(x[k], y[k]) << k;
       if (it == last_it) {
         const long long row0 = ((long long)first + (long long)it * step) * TILE + lrow0;
         unsigned valid = 0;
@@ -401,29 +409,38 @@ __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int l
           const unsigned B = b2[q] + (unsigned)(sb * stage2);
           const bool rimm = (kop2[q] & 0x100) != 0;
           const int op = kop2[q] & 0xff;
-          double x[K], y[K];
+          unsigned long long y[K];
 #pragma unroll
-          for (int k = 0; k < K; k++) x[k] = u2d(lds64(A + k * 256));
+          for (int k = 0; k < K; k++) v[k] = lds64(A + k * 256);
 #pragma unroll
-          for (int k = 0; k < K; k++) y[k] = rimm ? imm2[q] : u2d(lds64(B + k * 256));
-          if (op == V_ADD) {
+          for (int k = 0; k < K; k++) y[k] = rimm ? imm2[q] : lds64(B + k * 256);
+          if (kop2[q] & 0x200) {  // Int64 / UInt64: + - * (the host keeps integer division out of the fast shapes)
+            if (op == V_ADD) {
 #pragma unroll
-            for (int k = 0; k < K; k++) x[k] = x[k] + y[k];
+              for (int k = 0; k < K; k++) v[k] = v[k] + y[k];
+            } else if (op == V_MUL) {
+#pragma unroll
+              for (int k = 0; k < K; k++) v[k] = v[k] * y[k];
+            } else {
+#pragma unroll
+              for (int k = 0; k < K; k++) v[k] = v[k] - y[k];
+            }
+          } else if (op == V_ADD) {
+#pragma unroll
+            for (int k = 0; k < K; k++) v[k] = d2u(u2d(v[k]) + u2d(y[k]));
           } else if (op == V_MUL) {
 #pragma unroll
-            for (int k = 0; k < K; k++) x[k] = x[k] * y[k];
+            for (int k = 0; k < K; k++) v[k] = d2u(u2d(v[k]) * u2d(y[k]));
           } else if (op == V_SUB) {
 #pragma unroll
-            for (int k = 0; k < K; k++) x[k] = x[k] - y[k];
+            for (int k = 0; k < K; k++) v[k] = d2u(u2d(v[k]) - u2d(y[k]));
           } else {  // V_DIV
 #pragma unroll
             for (int k = 0; k < K; k++) {
-              if (y[k] == 0.0 && (flags & (1u << k))) bad = true;  // DivideByZero on a surviving row
-              x[k] = x[k] / y[k];
+              if (u2d(y[k]) == 0.0 && (flags & (1u << k))) bad = true;  // DivideByZero on a surviving row
+              v[k] = d2u(u2d(v[k]) / u2d(y[k]));
             }
           }
-#pragma unroll
-          for (int k = 0; k < K; k++) v[k] = d2u(x[k]);
         }
         if (q == 0) {
           unsigned run = 0;
@@ -442,14 +459,14 @@ __device__ __forceinline__ void consumer_lean(const FPParams& p, int warp, int l
   if (bad) *p.err_flag = 1u;
 }
 
-template <int K, int NP>
-__device__ __forceinline__ void consumer_lean_dispatch(const FPParams& p, int warp, int lane) {
+template <int K, int NP, int TY>
+__device__ __forceinline__ void consumer_lean_ops(const FPParams& p, int warp, int lane) {
   const int op = p.pred_fast.term[0].op;
   const bool pb = p.pred_fast.term[0].kind == 2;
-#define DF_LEAN(OP)                                            \
-  case OP:                                                     \
-    if (pb) consumer_lean<K, OP, true, NP>(p, warp, lane);     \
-    else consumer_lean<K, OP, false, NP>(p, warp, lane);       \
+#define DF_LEAN(OP)                                                \
+  case OP:                                                         \
+    if (pb) consumer_lean<K, OP, true, NP, TY>(p, warp, lane);     \
+    else consumer_lean<K, OP, false, NP, TY>(p, warp, lane);       \
     break;
   switch (op) {
     DF_LEAN(V_EQ)
@@ -458,11 +475,18 @@ __device__ __forceinline__ void consumer_lean_dispatch(const FPParams& p, int wa
     DF_LEAN(V_LE)
     DF_LEAN(V_GT)
     default:
-      if (pb) consumer_lean<K, V_GE, true, NP>(p, warp, lane);
-      else consumer_lean<K, V_GE, false, NP>(p, warp, lane);
+      if (pb) consumer_lean<K, V_GE, true, NP, TY>(p, warp, lane);
+      else consumer_lean<K, V_GE, false, NP, TY>(p, warp, lane);
       break;
   }
 #undef DF_LEAN
+}
+template <int K, int NP>
+__device__ __forceinline__ void consumer_lean_dispatch(const FPParams& p, int warp, int lane) {
+  const int ty = p.pred_fast.term[0].ty;
+  if (ty == DFGPU_FLOAT64) consumer_lean_ops<K, NP, 0>(p, warp, lane);
+  else if (ty == DFGPU_INT64) consumer_lean_ops<K, NP, 1>(p, warp, lane);
+  else consumer_lean_ops<K, NP, 2>(p, warp, lane);
 }
 
 // FAST: every program of the query is a fast shape, so the interpreter is not even compiled into
@@ -896,8 +920,10 @@ static void launch_k(dfgpu_ctx* ctx, const FPParams& p, size_t smem) {
   for (int q = 0; q < p.nproj; q++) fast = fast && p.proj_fast[q].kind > 0;
   bool all_f64 = true;
   for (int c = 0; c < p.ps.ncols; c++) all_f64 = all_f64 && p.ps.cols[c].dtype == DFGPU_FLOAT64;
-  // lean shapes: one Float64 comparison, one or two copy / arithmetic projections (DFGPU_FP_LEAN=0: A/B switch)
-  bool lean = fast && all_f64 && p.has_pred && p.pred_fast.nterms == 1 && p.nproj >= 1 && p.nproj <= LEAN_MAX_PROJ && !p.slab && !p.count_ballot;
+  // lean shapes: one comparison over 8-byte operands (Float64 / Int64 / UInt64), one or two copy / arithmetic projections over 8-byte columns (DFGPU_FP_LEAN=0: A/B switch)
+  auto w8 = [](int dt) { return dt == DFGPU_FLOAT64 || dt == DFGPU_INT64 || dt == DFGPU_UINT64; };
+  bool lean = fast && p.has_pred && p.pred_fast.nterms == 1 && w8(p.pred_fast.term[0].ty) && p.nproj >= 1 && p.nproj <= LEAN_MAX_PROJ && !p.slab && !p.count_ballot;
+  for (int q = 0; lean && q < p.nproj; q++) lean = w8(p.proj_fast[q].ty);  // copies and arithmetic over 8-byte columns only
   if (const char* e = getenv("DFGPU_FP_LEAN")) lean = lean && atoi(e) != 0;
   if (lean && p.nproj == 1) launch_one<1, K, true, true, false, 1>(ctx, p, smem);
   else if (lean) launch_one<1, K, true, true, false, 2>(ctx, p, smem);

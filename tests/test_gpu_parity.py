@@ -345,6 +345,35 @@ def test_lean_filter_shapes_all_operators(ctx):
         assert_cols_bit_equal(gpu_fp(ctx, [a2, z], col(0) > lit(0.25), [col(0) / col(1)]), O.filter_project([a2, z], col(0) > lit(0.25), [col(0) / col(1)]))
 
 
+@pytest.mark.parametrize("np_dt", [np.int64, np.uint64])
+def test_lean_filter_shapes_integer_operands(ctx, np_dt):
+    # the same loop with Int64 / UInt64 comparisons (signed vs unsigned order at the extremes), 64-bit wrap-around
+    # arithmetic in the projections, and a predicate over an integer column projecting a Float64 column
+    rng = np.random.default_rng(78)
+    n = 66_000
+    info = np.iinfo(np_dt)
+    a = rng.integers(info.min, info.max, n, dtype=np_dt, endpoint=True)
+    b = rng.integers(info.min, info.max, n, dtype=np_dt, endpoint=True)
+    a[::5] = rng.integers(0, 50, len(a[::5])).astype(np_dt)
+    b[::5] = rng.integers(0, 50, len(b[::5])).astype(np_dt)
+    a[::11] = info.max
+    b[::13] = info.min
+    f = rng.random(n)
+    dt = A.INT64 if np_dt == np.int64 else A.UINT64
+    preds = []
+    for rhs in (col(1), lit(25, dt)):
+        preds += [col(0) < rhs, col(0) <= rhs, col(0) > rhs, col(0) >= rhs, col(0).eq(rhs), col(0).not_eq(rhs)]
+    projs = [[col(0)], [col(2), col(1)], [col(0) + col(1), col(0) * col(1)], [col(0) - col(1)], [col(1) * lit(3, dt), col(2) * lit(0.5)],
+             [col(0) + lit(7, dt)]]
+    O.set_extensions(filter_all_primitives=True)  # the reference's filter() gathers Float64 / Utf8 only (filter.rs:82-108)
+    try:
+        for i, p in enumerate(preds):
+            pr = projs[i % len(projs)]
+            assert_cols_bit_equal(gpu_fp(ctx, [a, b, f], p, pr), O.filter_project([a, b, f], p, pr))
+    finally:
+        O.set_extensions(filter_all_primitives=False)
+
+
 def test_nan_and_signed_zero_compare(ctx):
     a = np.array([np.nan, 0.0, -0.0, 1.0, -np.inf, np.inf, np.nan, 5e-324] * 100)
     b = np.roll(a, 3)
