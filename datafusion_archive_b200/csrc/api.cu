@@ -580,6 +580,12 @@ extern "C" int dfgpu_result_col_device_ptr(const dfgpu_result* r, int i, const v
     *dptr = r->cols[size_t(i)].values;
   });
 }
+extern "C" int dfgpu_result_on_host(const dfgpu_result* r, int* on_host) {
+  return guarded([&] {
+    if (!r || !on_host) fail(DFGPU_ERR_GENERAL, "dfgpu_result_on_host: null argument");
+    *on_host = r->on_host ? 1 : 0;
+  });
+}
 extern "C" int dfgpu_result_col_host_ptr(const dfgpu_result* r, int i, const void** hptr) {
   return guarded([&] {
     if (i < 0 || size_t(i) >= r->cols.size()) fail(DFGPU_ERR_INVALID_COLUMN, "result column out of range");

@@ -564,10 +564,11 @@ extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, 
     if (pred_len > 0) scan(pred, pred_len);
     for (int q = 0; q < nproj; q++) scan(proj[q], proj_len[q]);
     if (used.empty()) fail(DFGPU_ERR_NOT_IMPLEMENTED, "queries that reference no column");
-    for (int c : used) {
-      if (!is_numeric(cols[c].dtype)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "dfgpu_filter_project_host handles fixed-width numeric columns only");
-      if (cols[c].validity) fail(DFGPU_ERR_NOT_IMPLEMENTED, "columns with nulls are not supported on the GPU path yet");
-    }
+    // Utf8 / Boolean / nullable inputs: not chunk-pipelined — the referenced columns are uploaded whole and the resident
+    // operator runs (same kernels, same results); the result then lives in DEVICE memory (dfgpu_result_on_host says
+    // which; dfgpu_result_copy_col works for both)
+    bool resident = false;
+    for (int c : used) resident = resident || !is_numeric(cols[c].dtype) || cols[c].validity;
     auto rewrite = [&](const dfgpu_insn* p, int len) {
       std::vector<dfgpu_insn> v(p, p + len);
       for (auto& in : v)
@@ -584,6 +585,20 @@ extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, 
     for (auto& v : proj2) {
       proj2p.push_back(v.data());
       proj2l.push_back(int(v.size()));
+    }
+    auto run_resident = [&] {
+      std::vector<dfgpu_col> sub;
+      for (int c : used) sub.push_back(cols[c]);
+      dfgpu_batch* b = nullptr;
+      int rc = dfgpu_batch_upload(ctx, sub.data(), int(sub.size()), &b);
+      if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+      struct G { dfgpu_batch* b; ~G() { dfgpu_batch_free(b); } } g{b};
+      rc = dfgpu_filter_project(ctx, b, pred2.data(), int(pred2.size()), proj2p.data(), proj2l.data(), nproj, out);
+      if (rc != DFGPU_OK) fail(rc, dfgpu_last_error());
+    };
+    if (resident) {
+      run_resident();
+      return;
     }
 
     if (chunk_rows <= 0) chunk_rows = 8ll << 20;
@@ -653,12 +668,16 @@ extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, 
         for (int q = 0; q < nproj; q++) {
           DevColumn hcol;
           hcol.dtype = ch.res->cols[size_t(q)].dtype;
-          if (!is_numeric(hcol.dtype)) fail(DFGPU_ERR_NOT_IMPLEMENTED, "dfgpu_filter_project_host returns fixed-width numeric columns only");
+          if (!is_numeric(hcol.dtype)) {  // Boolean projections (bit-packed): the resident operator handles the whole batch
+            resident = true;
+            break;
+          }
           hcol.values_bytes = size_t(n > 0 ? n : 1) * size_t(dtype_width(hcol.dtype));
           hcol.values = ctx->host_alloc(hcol.values_bytes);
           res->cols.push_back(hcol);
         }
       }
+      if (resident) break;
       // the kernel of this chunk has completed (dfgpu_filter_project synchronised ctx->stream)
       for (int q = 0; q < nproj; q++) {
         const int w = dtype_width(res->cols[size_t(q)].dtype);
@@ -669,6 +688,11 @@ extern "C" int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, 
       off += ch.res->nrows;
     }
     DF_CUDA(cudaStreamSynchronize(ctx->stream_out));
+    if (resident) {
+      res.reset();  // returns the pinned blocks of the projections before the Boolean one
+      run_resident();
+      return;
+    }
     res->nrows = off;
     *out = res.release();
   });

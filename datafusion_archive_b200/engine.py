@@ -68,6 +68,7 @@ def lib():
     L.dfgpu_filter_project.argtypes = [vp, vp, PI, C.c_int, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.dfgpu_filter_project_host.argtypes = [vp, C.POINTER(A.Col), C.c_int, PI, C.c_int, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.c_int64, C.POINTER(vp)]
     L.dfgpu_result_col_host_ptr.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.dfgpu_result_on_host.argtypes = [vp, C.POINTER(C.c_int)]
     L.dfgpu_aggregate_create.argtypes = [vp, C.POINTER(PI), C.POINTER(C.c_int), C.c_int, C.POINTER(A.Agg), C.c_int, C.c_int64, C.POINTER(vp)]
     L.dfgpu_aggregate_set_predicate.argtypes = [vp, PI, C.c_int]
     L.dfgpu_aggregate_update.argtypes = [vp, vp]
@@ -124,6 +125,13 @@ class Result:
         dt = C.c_int32()
         check(lib().dfgpu_result_col_dtype(self.h, i, C.byref(dt)))
         return dt.value
+
+    @property
+    def on_host(self):
+        """True when the columns live in pinned host memory (chunk-pipelined filter_project_host)."""
+        f = C.c_int()
+        check(lib().dfgpu_result_on_host(self.h, C.byref(f)))
+        return bool(f.value)
 
     def host_view(self, i):
         """Zero-copy numpy view of column i of a host-resident result (filter_project_host)."""

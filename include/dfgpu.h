@@ -186,8 +186,11 @@ int dfgpu_filter_project(dfgpu_ctx* ctx, const dfgpu_batch* batch, const dfgpu_i
  * row-range chunks and upload (H2D), kernel and download (D2H) of successive chunks overlap on three
  * streams; only the referenced columns cross PCIe.  This is what GpuFilterProjectRelation::next calls
  * for large batches.  The result's columns live in pinned host memory owned by the library
- * (dfgpu_result_col_host_ptr for zero-copy, dfgpu_result_copy_col to copy out); numeric outputs only.
- * Input buffers should be pinned (dfgpu_host_alloc) for the copies to be asynchronous. */
+ * (dfgpu_result_col_host_ptr for zero-copy, dfgpu_result_copy_col to copy out).
+ * Input buffers should be pinned (dfgpu_host_alloc) for the copies to be asynchronous.
+ * Batches whose referenced columns include Utf8, Boolean or nullable columns are not chunk-pipelined: the
+ * referenced columns are uploaded whole, the resident operator runs, and the result stays in device memory
+ * (dfgpu_result_on_host tells which; dfgpu_result_copy_col works for both). */
 int dfgpu_filter_project_host(dfgpu_ctx* ctx, const dfgpu_col* cols, int ncols, const dfgpu_insn* pred, int pred_len,
                               const dfgpu_insn* const* proj, const int* proj_len, int nproj, int64_t chunk_rows /*0 = default*/,
                               dfgpu_result** out);
@@ -227,7 +230,9 @@ int dfgpu_result_col_nulls(const dfgpu_result* r, int i, int64_t* null_count);
 /* Copy column i to host.  dst_values: nrows*width bytes (Utf8: nbytes); dst_validity: ceil(nrows/8)
  * bytes or NULL; dst_offsets: (nrows+1) i32 for Utf8, else NULL. */
 int dfgpu_result_copy_col(const dfgpu_result* r, int i, void* dst_values, uint8_t* dst_validity, int32_t* dst_offsets);
-/* Host pointer of column i's values (results of dfgpu_filter_project_host only). */
+/* 1 when the result's columns live in pinned host memory (the chunk-pipelined dfgpu_filter_project_host), else 0. */
+int dfgpu_result_on_host(const dfgpu_result* r, int* on_host);
+/* Host pointer of column i's values (host-resident results only). */
 int dfgpu_result_col_host_ptr(const dfgpu_result* r, int i, const void** hptr);
 /* Device pointer of column i's values (for zero-copy consumers on the same GPU). */
 int dfgpu_result_col_device_ptr(const dfgpu_result* r, int i, const void** dptr);

@@ -115,6 +115,7 @@ extern "C" {
     pub fn dfgpu_result_col_bytes(r: *const dfgpu_result, i: c_int, nbytes: *mut i64) -> c_int;
     pub fn dfgpu_result_col_nulls(r: *const dfgpu_result, i: c_int, nulls: *mut i64) -> c_int;
     pub fn dfgpu_result_copy_col(r: *const dfgpu_result, i: c_int, dst_values: *mut c_void, dst_validity: *mut u8, dst_offsets: *mut i32) -> c_int;
+    pub fn dfgpu_result_on_host(r: *const dfgpu_result, on_host: *mut c_int) -> c_int;
     pub fn dfgpu_result_col_host_ptr(r: *const dfgpu_result, i: c_int, hptr: *mut *const c_void) -> c_int;
     pub fn dfgpu_result_free(r: *mut dfgpu_result) -> c_int;
     pub fn dfgpu_comm_unique_id(out_id: *mut u8) -> c_int;

@@ -177,6 +177,38 @@ def test_host_pipelined_matches_resident_path(ctx):
     r = ctx.filter_project_host([np.array([], dtype=np.float64)], col(0) > lit(0.5), [col(0)])
     assert r.nrows == 0
     r.free()
+    # referenced Utf8 / nullable / Boolean columns: the same entry point runs the resident operator (device result)
+    import pyarrow as pa
+    rng = np.random.default_rng(5)
+    m = 200_000
+    x = rng.random(m)
+    names = ["n%05d" % (i % 977) for i in range(m)]
+    xn = pa.array(x, mask=rng.random(m) < 0.1)
+    flag = rng.random(m) < 0.5
+    for arrs, p_, pr in [([names, x], col(1) > lit(0.5), [col(0), col(1)]),
+                         ([xn, x], col(1) < lit(0.25), [col(0), col(0) + col(1)]),
+                         ([flag, x], col(0) & (col(1) > lit(0.5)), [col(1)])]:
+        r = ctx.filter_project_host(arrs, p_, pr)
+        assert not r.on_host
+        got = r.columns()
+        r.free()
+        exp = gpu_fp(ctx, arrs, p_, pr)
+        assert len(got) == len(exp)
+        for g, e in zip(got, exp):
+            if isinstance(g, tuple):
+                assert np.array_equal(g[1], e[1]) and np.array_equal(g[0][g[1]], e[0][e[1]])
+            elif isinstance(g, list):
+                assert g == e
+            else:
+                assert np.array_equal(g, e)
+    r = ctx.filter_project_host(arrays, pred, proj)
+    assert r.on_host
+    r.free()
+    r = ctx.filter_project_host([x], col(0) > lit(0.5), [col(0), col(0) < lit(0.75)], chunk_rows=50_000)  # a Boolean projection
+    assert not r.on_host
+    got = r.columns()
+    r.free()
+    assert np.array_equal(got[0], x[x > 0.5]) and np.array_equal(got[1], x[x > 0.5] < 0.75)
     with pytest.raises(engine.DfGpuError) as e:
         ctx.filter_project_host([pin.array], None, [col(0) / lit(0.0)])
     assert e.value.code == A.ERR_ARROW
