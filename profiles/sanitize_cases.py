@@ -49,6 +49,14 @@ arrays, pred, proj = workloads.c3(300_000)
 o = fp(arrays, pred, proj)
 m = arrays[1] < arrays[0]
 assert np.array_equal(o[0], (arrays[0] + arrays[1])[m]) and np.array_equal(o[1], (arrays[0] * arrays[1])[m])
+# lean consumer loop: Int64 comparison against a column, 64-bit integer arithmetic, two projections; generic FAST loop: two terms
+ki = rng.integers(-50, 50, 300_001, dtype=np.int64)
+kj = rng.integers(-50, 50, 300_001, dtype=np.int64)
+o = fp([ki, kj], col(0) <= col(1), [col(0) * col(1), col(1)])
+assert np.array_equal(o[0], (ki * kj)[ki <= kj]) and np.array_equal(o[1], kj[ki <= kj])
+a1 = rng.random(300_001)
+o = fp([a1], (col(0) > lit(0.25)) & (col(0) < lit(0.75)), [col(0)])
+assert np.array_equal(o[0], a1[(a1 > 0.25) & (a1 < 0.75)])
 # generic interpreter (direct kernel shapes)
 o = fp([arrays[0]], (col(0) * col(0)) < lit(0.3), [(col(0) + col(0)) * (col(0) - lit(1.0)) / (col(0) + lit(2.0))])
 a0 = arrays[0]
