@@ -363,6 +363,11 @@ def test_lean_filter_shapes_all_operators(ctx):
         for i, p in enumerate(preds):
             pr = projs[i % len(projs)]
             assert_cols_bit_equal(gpu_fp(ctx, [a, b], p, pr), O.filter_project([a, b], p, pr))
+        # six referenced columns: the 1024-row tile (K = 2) instantiation; four: the 2048-row one
+        c, d2, e, f = rng.random(n), rng.random(n), rng.random(n), rng.random(n)
+        for arrs, p_, pr in [([a, b, c, d2, e, f], col(0) < col(1), [col(2) + col(3), col(4) * col(5)]),
+                             ([a, b, c, d2], col(0) >= col(1), [col(2) - col(3), col(3)])]:
+            assert_cols_bit_equal(gpu_fp(ctx, arrs, p_, pr), O.filter_project(arrs, p_, pr))
         # division: fine while no surviving row divides by zero; DivideByZero otherwise (like the generic path)
         d = np.where(b == 0.0, 1.0, b)
         assert_cols_bit_equal(gpu_fp(ctx, [a, d], col(0) > lit(0.25), [col(0) / col(1)]), O.filter_project([a, d], col(0) > lit(0.25), [col(0) / col(1)]))
