@@ -121,6 +121,22 @@ extern "C" {
     pub fn dfgpu_comm_unique_id(out_id: *mut u8) -> c_int;
     pub fn dfgpu_comm_init(ctx: *mut dfgpu_ctx, rank: c_int, world: c_int, id: *const u8) -> c_int;
     pub fn dfgpu_comm_destroy(ctx: *mut dfgpu_ctx) -> c_int;
+    /// number of ranks of the attached communicator (1 without one): a rank whose input is empty still has to join
+    /// the merge of dfgpu_aggregate_finish (GpuAggregateRelation::next)
+    pub fn dfgpu_comm_world(ctx: *const dfgpu_ctx, world: *mut i64) -> c_int;
+    // ---- the rest of include/dfgpu.h (diagnostics, timing, zero-copy consumers), declared for completeness ----
+    pub fn dfgpu_device_count(out: *mut c_int) -> c_int;
+    pub fn dfgpu_sync(ctx: *mut dfgpu_ctx) -> c_int;
+    pub fn dfgpu_timer_start(ctx: *mut dfgpu_ctx) -> c_int;
+    pub fn dfgpu_timer_stop(ctx: *mut dfgpu_ctx, ms: *mut f32) -> c_int;
+    pub fn dfgpu_flush_l2(ctx: *mut dfgpu_ctx) -> c_int;
+    pub fn dfgpu_kernel_launches(ctx: *const dfgpu_ctx, out: *mut i64) -> c_int;
+    pub fn dfgpu_profile_enable(ctx: *mut dfgpu_ctx, on: c_int) -> c_int;
+    pub fn dfgpu_profile_get(ctx: *mut dfgpu_ctx, kernel_ms: *mut f64, launches: *mut i64) -> c_int;
+    pub fn dfgpu_batch_rows(b: *const dfgpu_batch, nrows: *mut i64) -> c_int;
+    /// type check of one expression program without a device (the checks compile_scalar_expr makes: expression.rs:136-290)
+    pub fn dfgpu_check_program(col_dtypes: *const i32, ncols: c_int, prog: *const dfgpu_insn, prog_len: c_int, out_dtype: *mut i32) -> c_int;
+    pub fn dfgpu_result_col_device_ptr(r: *const dfgpu_result, i: c_int, dptr: *mut *const c_void) -> c_int;
 }
 
 /// nonzero status -> ExecutionError (src/execution/error.rs:51-60)

@@ -80,3 +80,23 @@ def test_product_does_not_reference_oracle():
         if os.path.exists(path):
             assert "oracle" not in subprocess.run(["ldd", path], capture_output=True, text=True).stdout
 
+
+
+def test_rust_shim_declares_every_entry_point():
+    # shim/src/execution/gpu/ffi.rs is the `extern "C"` block a maintainer adds to the reference:
+    # it has to name every function of include/dfgpu.h, with the same number of parameters
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "dfgpu.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    ffi = open(os.path.join(root, "shim", "src", "execution", "gpu", "ffi.rs")).read()
+    ffi = re.sub(r"//[^\n]*", "", ffi)
+    cdecl = {m.group(1): m.group(2) for m in re.finditer(r"\b(dfgpu_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)}
+    rdecl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (dfgpu_[a-z0-9_]+)\s*\((.*?)\)\s*->", ffi, flags=re.S)}
+    assert len(cdecl) >= 39
+    for name, params in cdecl.items():
+        assert name in rdecl, "%s is not declared in shim/src/execution/gpu/ffi.rs" % name
+        nc = 0 if params.strip() in ("", "void") else params.count(",") + 1
+        rp = rdecl[name].strip().rstrip(",")
+        nr = 0 if not rp else rp.count(",") + 1
+        assert nc == nr, "%s: %d parameters in the header, %d in ffi.rs" % (name, nc, nr)
