@@ -289,7 +289,37 @@ impl Relation for GpuAggregateRelation {
             if st.is_null() {
                 // empty input: GROUP BY -> empty batch; no GROUP BY -> one row of nulls (array_from_scalar!, aggregate.rs:641-643)
                 if !self.group_expr.is_empty() {
-                    return Ok(RecordBatch::new(self.schema.clone(), vec![]));
+                    let mut world: i64 = 1;
+                    check(unsafe { dfgpu_comm_world(self.gpu.raw, &mut world) })?;
+                    if world <= 1 {
+                        return Ok(RecordBatch::new(self.schema.clone(), vec![]));
+                    }
+                    // a communicator is attached: this rank saw no batch but still has to join the merge of
+                    // dfgpu_aggregate_finish with an empty state (it adopts the key / argument types from the other ranks)
+                    let (_, remap) = prune(&reads, in_schema.fields().len(), false);
+                    let mut keys: Vec<Vec<dfgpu_insn>> = vec![];
+                    for k in &self.group_expr {
+                        let mut v = vec![];
+                        lower(k, &in_schema, &remap, &mut v)?;
+                        keys.push(v);
+                    }
+                    let mut arg_progs: Vec<Vec<dfgpu_insn>> = vec![];
+                    for a in &args {
+                        let mut v = vec![];
+                        lower(a.1, &in_schema, &remap, &mut v)?;
+                        arg_progs.push(v);
+                    }
+                    let kptr: Vec<*const dfgpu_insn> = keys.iter().map(|p| p.as_ptr()).collect();
+                    let klen: Vec<c_int> = keys.iter().map(|p| p.len() as c_int).collect();
+                    let aggs: Vec<dfgpu_agg> = args.iter().zip(arg_progs.iter())
+                        .map(|(a, p)| dfgpu_agg { func: a.0, arg_len: p.len() as i32, arg: p.as_ptr(), out_dtype: a.2, _pad: 0 })
+                        .collect();
+                    check(unsafe { dfgpu_aggregate_create(self.gpu.raw, kptr.as_ptr(), klen.as_ptr(), kptr.len() as c_int, aggs.as_ptr(), aggs.len() as c_int, 0, &mut st) })?;
+                    let mut res = ptr::null_mut();
+                    check(unsafe { dfgpu_aggregate_finish(st, &mut res) })?;
+                    let out = download(res, &self.schema);
+                    unsafe { dfgpu_result_free(res) };
+                    return out;
                 }
                 let lit = [dfgpu_insn { op: OP_COL, col: 0, dtype: 0, _pad: 0, lit: 0 }];
                 let aggs: Vec<dfgpu_agg> = args.iter().map(|a| dfgpu_agg { func: a.0, arg_len: 1, arg: lit.as_ptr(), out_dtype: a.2, _pad: 0 }).collect();
