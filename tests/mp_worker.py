@@ -4,7 +4,7 @@
               its partial aggregate by owner rank, the segments travel over gloo, every rank merges only
               the keys it owns, the owned segments are gathered, and the result is checked against the
               oracle on the full data.  Exercises row ranges, the owner function and the merge algebra
-              without a GPU.
+              without a GPU; likewise a model of the regroup merge used for Utf8 / wide keys.
   mode nccl : GPUs.  Each rank drives its own B200 through the C ABI with a communicator attached;
               every rank must end with the SAME global result (dfgpu_aggregate_finish: owner-partitioned
               exchange over NCCL), also when one rank saw no rows at all.
@@ -76,6 +76,31 @@ def main():
         fg = [None] * world
         dist.all_gather_object(fg, fpart)
         fout = parallel.concat_in_rank_order(fg)
+        # regroup merge (Utf8 / wide keys, aggregate.cu finish_regroup), MODEL: every rank's LOCAL RESULT is gathered and
+        # aggregated once more with each aggregate's merge function (COUNT -> SUM of the counts)
+        rng = np.random.default_rng(99)
+        wn = 60_000
+        wk1 = workloads.mix_keys(rng.integers(0, 150, wn, dtype=np.int64))
+        wk2 = rng.integers(-(2 ** 62), 2 ** 62, 20, dtype=np.int64)[rng.integers(0, 20, wn)]
+        ws = ["s%03d" % i for i in rng.integers(0, 40, wn)]
+        wv = rng.random(wn)
+        wlo, whi = parallel.row_range(rank, world, wn)
+        for cols_, nk in (([wk1, wk2, wv], 2), ([ws, wv], 1)):
+            wkeys = [col(i) for i in range(nk)]
+            wa = [AggregateFunction("min", col(nk)), AggregateFunction("max", col(nk)), AggregateFunction("sum", col(nk)), AggregateFunction("count", col(nk))]
+            local = O.aggregate([c[wlo:whi] for c in cols_], wkeys, wa)
+            allres = [None] * world
+            dist.all_gather_object(allres, [c if isinstance(c, list) else np.asarray(c) for c in local])
+            cat = [sum((r[i] for r in allres), []) if isinstance(allres[0][i], list) else np.concatenate([r[i] for r in allres]) for i in range(nk + 4)]
+            merge = [AggregateFunction("min", col(nk)), AggregateFunction("max", col(nk + 1)), AggregateFunction("sum", col(nk + 2)), AggregateFunction("sum", col(nk + 3))]
+            got = O.aggregate(cat, wkeys, merge)
+            exp = O.aggregate(cols_, wkeys, wa)
+            rows = lambda cs: sorted(zip(*[c if isinstance(c, list) else c.tolist() for c in cs]), key=lambda r: r[:nk])  # noqa: E731
+            g, e = rows(got), rows(exp)
+            assert len(g) == len(e)
+            for rg, re_ in zip(g, e):
+                assert rg[:nk + 2] == re_[:nk + 2] and rg[nk + 3] == re_[nk + 3], (rg, re_)
+                assert abs(rg[nk + 2] - re_[nk + 2]) <= 1e-9 * abs(re_[nk + 2]), (rg, re_)
         # no GROUP BY: scalars combine with the same algebra
         spart = O.aggregate(mine, [], aggs)
         sg = [None] * world
